@@ -1,0 +1,447 @@
+// fq.cuh -- BN254 base field Fq on 8 x 32-bit limbs, Montgomery form (R = 2^256), one thread per element.
+//
+// Replaces the `Fq` type of the reference's arithmetic dependency (crate zeropool-bn 0.5.11, imported as `bn`
+// at /root/reference/Cargo.toml:24; call sites /root/reference/src/utils.rs:44,88-90,111-112).  Values are
+// always kept fully reduced in [0, q), so two implementations that agree on the field value agree on the bits.
+//
+// Device path: the multiplication is a 32-bit CIOS Montgomery product written as PTX carry chains in the
+// "even/odd accumulator" arrangement: every (mad.lo.cc, madc.hi.cc) pair on the same operands sits on one carry
+// chain, which ptxas fuses into a single IMAD.WIDE.U32.X with predicate carry-in/out -- 128 wide multiply-adds
+// + 8 IMAD for the quotient digits per product.  The same header compiles as plain C++ (g++) for the CPU-side
+// simulation used by tests/hostsim: there the portable 64-bit code path below is used instead of PTX.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define BN_FN __device__ __forceinline__
+#define BN_NOINLINE __device__ __noinline__
+#define BN_CONST __constant__ const
+#else
+#define BN_FN static inline
+#define BN_NOINLINE static __attribute__((noinline))
+#define BN_CONST static const
+#endif
+
+#include "constants.cuh"
+
+namespace bn {
+
+struct alignas(16) fq {
+  uint32_t l[8];
+};
+
+// q limbs as literals (immediates in SASS)
+#define BN_Q0 0xd87cfd47u
+#define BN_Q1 0x3c208c16u
+#define BN_Q2 0x6871ca8du
+#define BN_Q3 0x97816a91u
+#define BN_Q4 0x8181585du
+#define BN_Q5 0xb85045b6u
+#define BN_Q6 0xe131a029u
+#define BN_Q7 0x30644e72u
+
+BN_FN fq fq_zero() {
+  fq r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.l[i] = 0;
+  return r;
+}
+BN_FN fq fq_from_limbs(const uint32_t* p) {
+  fq r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.l[i] = p[i];
+  return r;
+}
+BN_FN fq fq_one() { return fq_from_limbs(K_ONE); }
+BN_FN bool fq_is_zero(const fq& a) {
+  uint32_t t = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) t |= a.l[i];
+  return t == 0;
+}
+BN_FN bool fq_eq(const fq& a, const fq& b) {
+  uint32_t t = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) t |= a.l[i] ^ b.l[i];
+  return t == 0;
+}
+// plain 256-bit compare helpers on limb arrays: a >= b
+BN_FN bool u256_geq(const uint32_t* a, const uint32_t* b) {
+  uint32_t borrow = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    uint64_t t = (uint64_t)a[i] - b[i] - borrow;
+    borrow = (uint32_t)(t >> 63);
+  }
+  return borrow == 0;
+}
+// r = a - b, returns borrow
+BN_FN uint32_t u256_sub(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  uint32_t borrow = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    uint64_t t = (uint64_t)a[i] - b[i] - borrow;
+    r[i] = (uint32_t)t;
+    borrow = (uint32_t)(t >> 63);
+  }
+  return borrow;
+}
+
+// ------------------------------------------------------------------------------------------------ add / sub
+#if defined(__CUDA_ARCH__)
+BN_FN fq fq_add(const fq& a, const fq& b) {
+  uint32_t s0, s1, s2, s3, s4, s5, s6, s7, t0, t1, t2, t3, t4, t5, t6, t7, bw;
+  asm("add.cc.u32 %0, %8, %16;\n\t"
+      "addc.cc.u32 %1, %9, %17;\n\t"
+      "addc.cc.u32 %2, %10, %18;\n\t"
+      "addc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\t"
+      "addc.cc.u32 %5, %13, %21;\n\t"
+      "addc.cc.u32 %6, %14, %22;\n\t"
+      "addc.u32 %7, %15, %23;\n\t"
+      : "=r"(s0), "=r"(s1), "=r"(s2), "=r"(s3), "=r"(s4), "=r"(s5), "=r"(s6), "=r"(s7)
+      : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]),
+        "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
+  asm("sub.cc.u32 %0, %9, 0xd87cfd47;\n\t"
+      "subc.cc.u32 %1, %10, 0x3c208c16;\n\t"
+      "subc.cc.u32 %2, %11, 0x6871ca8d;\n\t"
+      "subc.cc.u32 %3, %12, 0x97816a91;\n\t"
+      "subc.cc.u32 %4, %13, 0x8181585d;\n\t"
+      "subc.cc.u32 %5, %14, 0xb85045b6;\n\t"
+      "subc.cc.u32 %6, %15, 0xe131a029;\n\t"
+      "subc.cc.u32 %7, %16, 0x30644e72;\n\t"
+      "subc.u32 %8, 0, 0;\n\t"
+      : "=r"(t0), "=r"(t1), "=r"(t2), "=r"(t3), "=r"(t4), "=r"(t5), "=r"(t6), "=r"(t7), "=r"(bw)
+      : "r"(s0), "r"(s1), "r"(s2), "r"(s3), "r"(s4), "r"(s5), "r"(s6), "r"(s7));
+  fq r;
+  bool keep = bw != 0;  // borrow: a + b < q
+  r.l[0] = keep ? s0 : t0; r.l[1] = keep ? s1 : t1; r.l[2] = keep ? s2 : t2; r.l[3] = keep ? s3 : t3;
+  r.l[4] = keep ? s4 : t4; r.l[5] = keep ? s5 : t5; r.l[6] = keep ? s6 : t6; r.l[7] = keep ? s7 : t7;
+  return r;
+}
+BN_FN fq fq_sub(const fq& a, const fq& b) {
+  uint32_t d0, d1, d2, d3, d4, d5, d6, d7, m;
+  asm("sub.cc.u32 %0, %9, %17;\n\t"
+      "subc.cc.u32 %1, %10, %18;\n\t"
+      "subc.cc.u32 %2, %11, %19;\n\t"
+      "subc.cc.u32 %3, %12, %20;\n\t"
+      "subc.cc.u32 %4, %13, %21;\n\t"
+      "subc.cc.u32 %5, %14, %22;\n\t"
+      "subc.cc.u32 %6, %15, %23;\n\t"
+      "subc.cc.u32 %7, %16, %24;\n\t"
+      "subc.u32 %8, 0, 0;\n\t"
+      : "=r"(d0), "=r"(d1), "=r"(d2), "=r"(d3), "=r"(d4), "=r"(d5), "=r"(d6), "=r"(d7), "=r"(m)
+      : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]),
+        "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
+  fq r;
+  asm("add.cc.u32 %0, %8, %16;\n\t"
+      "addc.cc.u32 %1, %9, %17;\n\t"
+      "addc.cc.u32 %2, %10, %18;\n\t"
+      "addc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\t"
+      "addc.cc.u32 %5, %13, %21;\n\t"
+      "addc.cc.u32 %6, %14, %22;\n\t"
+      "addc.u32 %7, %15, %23;\n\t"
+      : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7])
+      : "r"(d0), "r"(d1), "r"(d2), "r"(d3), "r"(d4), "r"(d5), "r"(d6), "r"(d7),
+        "r"(m & BN_Q0), "r"(m & BN_Q1), "r"(m & BN_Q2), "r"(m & BN_Q3), "r"(m & BN_Q4), "r"(m & BN_Q5), "r"(m & BN_Q6), "r"(m & BN_Q7));
+  return r;
+}
+#else
+BN_FN fq fq_add(const fq& a, const fq& b) {
+  fq s, t;
+  uint64_t c = 0;
+  for (int i = 0; i < 8; i++) {
+    c += (uint64_t)a.l[i] + b.l[i];
+    s.l[i] = (uint32_t)c;
+    c >>= 32;
+  }
+  uint32_t bw = u256_sub(t.l, s.l, K_Q);
+  return bw ? s : t;
+}
+BN_FN fq fq_sub(const fq& a, const fq& b) {
+  fq d;
+  uint32_t bw = u256_sub(d.l, a.l, b.l);
+  if (bw) {
+    uint64_t c = 0;
+    for (int i = 0; i < 8; i++) {
+      c += (uint64_t)d.l[i] + K_Q[i];
+      d.l[i] = (uint32_t)c;
+      c >>= 32;
+    }
+  }
+  return d;
+}
+#endif
+BN_FN fq fq_dbl(const fq& a) { return fq_add(a, a); }
+BN_FN fq fq_neg(const fq& a) { return fq_sub(fq_zero(), a); }
+
+// ------------------------------------------------------------------------------------------------ Montgomery product
+// portable CIOS (host simulation; also kept on the device as the cross-check variant of the PTX product)
+BN_FN fq fq_mul_portable(const fq& a, const fq& b) {
+  uint32_t t[10];
+#pragma unroll
+  for (int i = 0; i < 10; i++) t[i] = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    uint64_t c = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      c += (uint64_t)a.l[j] * b.l[i] + t[j];
+      t[j] = (uint32_t)c;
+      c >>= 32;
+    }
+    c += t[8];
+    t[8] = (uint32_t)c;
+    t[9] = (uint32_t)(c >> 32);
+    uint32_t m = t[0] * K_QINV_NEG;
+    const uint32_t qq[8] = {BN_Q0, BN_Q1, BN_Q2, BN_Q3, BN_Q4, BN_Q5, BN_Q6, BN_Q7};
+    c = (uint64_t)m * qq[0] + t[0];
+    c >>= 32;
+#pragma unroll
+    for (int j = 1; j < 8; j++) {
+      c += (uint64_t)m * qq[j] + t[j];
+      t[j - 1] = (uint32_t)c;
+      c >>= 32;
+    }
+    c += t[8];
+    t[7] = (uint32_t)c;
+    t[8] = t[9] + (uint32_t)(c >> 32);
+  }
+  fq s, r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s.l[i] = t[i];
+  const uint32_t qq[8] = {BN_Q0, BN_Q1, BN_Q2, BN_Q3, BN_Q4, BN_Q5, BN_Q6, BN_Q7};
+  uint32_t bw = u256_sub(r.l, s.l, qq);
+  bool keep = (t[8] == 0) && bw;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.l[i] = keep ? s.l[i] : r.l[i];
+  return r;
+}
+
+#if defined(__CUDA_ARCH__)
+namespace detail {
+// Y[0..7] sits at limb columns c..c+7, X[0..7] at c+1..c+8 ("even" and "odd" accumulators).
+// first row: Y = a_even * w, X = a_odd * w
+BN_FN void mont_row_first(uint32_t* Y, uint32_t* X, const uint32_t* a, uint32_t w) {
+  asm("mul.lo.u32 %0, %8, %12;\n\t"
+      "mul.hi.u32 %1, %8, %12;\n\t"
+      "mul.lo.u32 %2, %9, %12;\n\t"
+      "mul.hi.u32 %3, %9, %12;\n\t"
+      "mul.lo.u32 %4, %10, %12;\n\t"
+      "mul.hi.u32 %5, %10, %12;\n\t"
+      "mul.lo.u32 %6, %11, %12;\n\t"
+      "mul.hi.u32 %7, %11, %12;\n\t"
+      : "=r"(Y[0]), "=r"(Y[1]), "=r"(Y[2]), "=r"(Y[3]), "=r"(Y[4]), "=r"(Y[5]), "=r"(Y[6]), "=r"(Y[7])
+      : "r"(a[0]), "r"(a[2]), "r"(a[4]), "r"(a[6]), "r"(w));
+  asm("mul.lo.u32 %0, %8, %12;\n\t"
+      "mul.hi.u32 %1, %8, %12;\n\t"
+      "mul.lo.u32 %2, %9, %12;\n\t"
+      "mul.hi.u32 %3, %9, %12;\n\t"
+      "mul.lo.u32 %4, %10, %12;\n\t"
+      "mul.hi.u32 %5, %10, %12;\n\t"
+      "mul.lo.u32 %6, %11, %12;\n\t"
+      "mul.hi.u32 %7, %11, %12;\n\t"
+      : "=r"(X[0]), "=r"(X[1]), "=r"(X[2]), "=r"(X[3]), "=r"(X[4]), "=r"(X[5]), "=r"(X[6]), "=r"(X[7])
+      : "r"(a[1]), "r"(a[3]), "r"(a[5]), "r"(a[7]), "r"(w));
+}
+// later rows: Y is the accumulator aligned at the new base column, X is the previous base-aligned accumulator
+// (its limb 0 was cleared by the reduction): fold X[1] into Y[0], shift X down two limbs while adding a_odd*w,
+// then Y += a_even*w with the carry-out going to X[7].
+BN_FN void mont_row_next(uint32_t* Y, uint32_t* X, const uint32_t* a, uint32_t w) {
+  asm("add.cc.u32 %0, %0, %2;\n\t"
+      "madc.lo.cc.u32 %1, %9, %13, %3;\n\t"
+      "madc.hi.cc.u32 %2, %9, %13, %4;\n\t"
+      "madc.lo.cc.u32 %3, %10, %13, %5;\n\t"
+      "madc.hi.cc.u32 %4, %10, %13, %6;\n\t"
+      "madc.lo.cc.u32 %5, %11, %13, %7;\n\t"
+      "madc.hi.cc.u32 %6, %11, %13, %8;\n\t"
+      "madc.lo.cc.u32 %7, %12, %13, 0;\n\t"
+      "madc.hi.u32 %8, %12, %13, 0;\n\t"
+      : "+r"(Y[0]), "+r"(X[0]), "+r"(X[1]), "+r"(X[2]), "+r"(X[3]), "+r"(X[4]), "+r"(X[5]), "+r"(X[6]), "+r"(X[7])
+      : "r"(a[1]), "r"(a[3]), "r"(a[5]), "r"(a[7]), "r"(w));
+  asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+      "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+      "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+      "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+      "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+      "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+      "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+      "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+      "addc.u32 %8, %8, 0;\n\t"
+      : "+r"(Y[0]), "+r"(Y[1]), "+r"(Y[2]), "+r"(Y[3]), "+r"(Y[4]), "+r"(Y[5]), "+r"(Y[6]), "+r"(Y[7]), "+r"(X[7])
+      : "r"(a[0]), "r"(a[2]), "r"(a[4]), "r"(a[6]), "r"(w));
+}
+// Montgomery reduction of the lowest limb: m = Y[0] * (-q^-1); X += q_odd * m; Y += q_even * m (Y[0] becomes 0)
+BN_FN void mont_reduce_row(uint32_t* Y, uint32_t* X) {
+  uint32_t m = Y[0] * K_QINV_NEG;
+  asm("mad.lo.cc.u32 %0, %8, 0x3c208c16, %0;\n\t"
+      "madc.hi.cc.u32 %1, %8, 0x3c208c16, %1;\n\t"
+      "madc.lo.cc.u32 %2, %8, 0x97816a91, %2;\n\t"
+      "madc.hi.cc.u32 %3, %8, 0x97816a91, %3;\n\t"
+      "madc.lo.cc.u32 %4, %8, 0xb85045b6, %4;\n\t"
+      "madc.hi.cc.u32 %5, %8, 0xb85045b6, %5;\n\t"
+      "madc.lo.cc.u32 %6, %8, 0x30644e72, %6;\n\t"
+      "madc.hi.u32 %7, %8, 0x30644e72, %7;\n\t"
+      : "+r"(X[0]), "+r"(X[1]), "+r"(X[2]), "+r"(X[3]), "+r"(X[4]), "+r"(X[5]), "+r"(X[6]), "+r"(X[7])
+      : "r"(m));
+  asm("mad.lo.cc.u32 %0, %9, 0xd87cfd47, %0;\n\t"
+      "madc.hi.cc.u32 %1, %9, 0xd87cfd47, %1;\n\t"
+      "madc.lo.cc.u32 %2, %9, 0x6871ca8d, %2;\n\t"
+      "madc.hi.cc.u32 %3, %9, 0x6871ca8d, %3;\n\t"
+      "madc.lo.cc.u32 %4, %9, 0x8181585d, %4;\n\t"
+      "madc.hi.cc.u32 %5, %9, 0x8181585d, %5;\n\t"
+      "madc.lo.cc.u32 %6, %9, 0xe131a029, %6;\n\t"
+      "madc.hi.cc.u32 %7, %9, 0xe131a029, %7;\n\t"
+      "addc.u32 %8, %8, 0;\n\t"
+      : "+r"(Y[0]), "+r"(Y[1]), "+r"(Y[2]), "+r"(Y[3]), "+r"(Y[4]), "+r"(Y[5]), "+r"(Y[6]), "+r"(Y[7]), "+r"(X[7])
+      : "r"(m));
+}
+// final merge + conditional subtraction: res[k] = X[k] + Y[k+1]; value < 2q
+BN_FN fq mont_finish(const uint32_t* X, const uint32_t* Y) {
+  uint32_t s0, s1, s2, s3, s4, s5, s6, s7, t0, t1, t2, t3, t4, t5, t6, t7, bw;
+  asm("add.cc.u32 %0, %8, %16;\n\t"
+      "addc.cc.u32 %1, %9, %17;\n\t"
+      "addc.cc.u32 %2, %10, %18;\n\t"
+      "addc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\t"
+      "addc.cc.u32 %5, %13, %21;\n\t"
+      "addc.cc.u32 %6, %14, %22;\n\t"
+      "addc.u32 %7, %15, 0;\n\t"
+      : "=r"(s0), "=r"(s1), "=r"(s2), "=r"(s3), "=r"(s4), "=r"(s5), "=r"(s6), "=r"(s7)
+      : "r"(X[0]), "r"(X[1]), "r"(X[2]), "r"(X[3]), "r"(X[4]), "r"(X[5]), "r"(X[6]), "r"(X[7]),
+        "r"(Y[1]), "r"(Y[2]), "r"(Y[3]), "r"(Y[4]), "r"(Y[5]), "r"(Y[6]), "r"(Y[7]));
+  asm("sub.cc.u32 %0, %9, 0xd87cfd47;\n\t"
+      "subc.cc.u32 %1, %10, 0x3c208c16;\n\t"
+      "subc.cc.u32 %2, %11, 0x6871ca8d;\n\t"
+      "subc.cc.u32 %3, %12, 0x97816a91;\n\t"
+      "subc.cc.u32 %4, %13, 0x8181585d;\n\t"
+      "subc.cc.u32 %5, %14, 0xb85045b6;\n\t"
+      "subc.cc.u32 %6, %15, 0xe131a029;\n\t"
+      "subc.cc.u32 %7, %16, 0x30644e72;\n\t"
+      "subc.u32 %8, 0, 0;\n\t"
+      : "=r"(t0), "=r"(t1), "=r"(t2), "=r"(t3), "=r"(t4), "=r"(t5), "=r"(t6), "=r"(t7), "=r"(bw)
+      : "r"(s0), "r"(s1), "r"(s2), "r"(s3), "r"(s4), "r"(s5), "r"(s6), "r"(s7));
+  fq r;
+  bool keep = bw != 0;
+  r.l[0] = keep ? s0 : t0; r.l[1] = keep ? s1 : t1; r.l[2] = keep ? s2 : t2; r.l[3] = keep ? s3 : t3;
+  r.l[4] = keep ? s4 : t4; r.l[5] = keep ? s5 : t5; r.l[6] = keep ? s6 : t6; r.l[7] = keep ? s7 : t7;
+  return r;
+}
+}  // namespace detail
+
+BN_FN fq fq_mul_ptx(const fq& a, const fq& b) {
+  uint32_t E[8], O[8];
+  detail::mont_row_first(E, O, a.l, b.l[0]);
+  detail::mont_reduce_row(E, O);
+  detail::mont_row_next(O, E, a.l, b.l[1]);
+  detail::mont_reduce_row(O, E);
+  detail::mont_row_next(E, O, a.l, b.l[2]);
+  detail::mont_reduce_row(E, O);
+  detail::mont_row_next(O, E, a.l, b.l[3]);
+  detail::mont_reduce_row(O, E);
+  detail::mont_row_next(E, O, a.l, b.l[4]);
+  detail::mont_reduce_row(E, O);
+  detail::mont_row_next(O, E, a.l, b.l[5]);
+  detail::mont_reduce_row(O, E);
+  detail::mont_row_next(E, O, a.l, b.l[6]);
+  detail::mont_reduce_row(E, O);
+  detail::mont_row_next(O, E, a.l, b.l[7]);
+  detail::mont_reduce_row(O, E);
+  return detail::mont_finish(E, O);
+}
+#endif
+
+#if defined(__CUDA_ARCH__) && !defined(BN254_PORTABLE_MUL)
+BN_FN fq fq_mul(const fq& a, const fq& b) { return fq_mul_ptx(a, b); }
+#else
+BN_FN fq fq_mul(const fq& a, const fq& b) { return fq_mul_portable(a, b); }
+#endif
+BN_FN fq fq_sqr(const fq& a) { return fq_mul(a, a); }
+
+// out-of-line copies: used where code size matters more than the call
+BN_NOINLINE void fq_mul_ni(fq* r, const fq* a, const fq* b) { *r = fq_mul(*a, *b); }
+
+// ------------------------------------------------------------------------------------------------ conversions
+BN_FN fq fq_to_mont(const fq& a) { return fq_mul(a, fq_from_limbs(K_R2)); }
+BN_FN fq fq_from_mont(const fq& a) {
+  fq one = fq_zero();
+  one.l[0] = 1;
+  return fq_mul(a, one);
+}
+BN_FN uint32_t bswap32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  return __byte_perm(x, 0, 0x0123);
+#else
+  return __builtin_bswap32(x);
+#endif
+}
+// 32 big-endian bytes -> plain limbs (no reduction, no Montgomery)
+BN_FN void u256_from_be(uint32_t* l, const uint8_t* b) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const uint8_t* p = b + 4 * (7 - i);
+    l[i] = ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3];
+  }
+}
+BN_FN void u256_to_be(uint8_t* b, const uint32_t* l) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    uint8_t* p = b + 4 * (7 - i);
+    p[0] = (uint8_t)(l[i] >> 24); p[1] = (uint8_t)(l[i] >> 16); p[2] = (uint8_t)(l[i] >> 8); p[3] = (uint8_t)l[i];
+  }
+}
+// Fq::from_slice: value >= q -> false (NotMember)
+BN_FN bool fq_from_be(fq* r, const uint8_t* b) {
+  fq t;
+  u256_from_be(t.l, b);
+  if (u256_geq(t.l, K_Q)) return false;
+  *r = fq_to_mont(t);
+  return true;
+}
+BN_FN void fq_to_be(uint8_t* b, const fq& a) {
+  fq t = fq_from_mont(a);
+  u256_to_be(b, t.l);
+}
+
+// ------------------------------------------------------------------------------------------------ fixed exponents
+// a^e for a public exponent e (8 limbs), 4-bit fixed windows, MSB first.  Control flow depends on e only.
+BN_NOINLINE void fq_pow_pub(fq* r, const fq* a, const uint32_t* e) {
+  fq tab[16];
+  tab[0] = fq_one();
+  tab[1] = *a;
+  for (int i = 2; i < 16; i++) fq_mul_ni(&tab[i], &tab[i - 1], a);
+  fq acc = fq_one();
+  bool started = false;
+  for (int w = 63; w >= 0; w--) {
+    uint32_t nib = (e[w >> 3] >> ((w & 7) * 4)) & 15;
+    if (started) {
+      for (int k = 0; k < 4; k++) fq_mul_ni(&acc, &acc, &acc);
+    }
+    if (nib) {
+      if (started) fq_mul_ni(&acc, &acc, &tab[nib]);
+      else acc = tab[nib];
+      started = true;
+    }
+  }
+  *r = acc;
+}
+BN_FN fq fq_inv(const fq& a) {
+  fq r;
+  fq_pow_pub(&r, &a, K_EXP_QM2);
+  return r;
+}
+// Fq::sqrt of the dependency: a1 = a^((q-3)/4); root = a1*a; reject iff a1*root == -1
+BN_FN bool fq_sqrt(fq* root, const fq& a) {
+  fq a1;
+  fq_pow_pub(&a1, &a, K_EXP_QM3D4);
+  fq rt = fq_mul(a1, a);
+  fq chk = fq_mul(a1, rt);
+  if (fq_eq(chk, fq_neg(fq_one()))) return false;
+  *root = rt;
+  return true;
+}
+// canonical parity of y (Montgomery in)
+BN_FN uint32_t fq_parity(const fq& a) { return fq_from_mont(a).l[0] & 1; }
+
+}  // namespace bn

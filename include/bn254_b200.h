@@ -1,0 +1,136 @@
+/*
+ * bn254_b200.h -- C ABI of the B200-native BN254 batch engine (libbn254_b200.so).
+ *
+ * This is the drop-in boundary for the sign / aggregate / pairing-verify hot path of sedaprotocol/bn254.
+ * The reference has no FFI of its own: its boundary is the Rust public API re-exported at
+ * /root/reference/src/lib.rs:60-63.  Each entry point below names the reference item it replaces; a thin Rust
+ * wrapper keeps the crate's types (PrivateKey / PublicKey / PublicKeyG1 / Signature, ECDSA::sign / verify,
+ * + - aggregation) and converts through the crate's own big-endian byte formats.
+ *
+ * Conventions
+ *   - Every integer is 32-byte big-endian canonical.  A G1 point is x||y (64 B, the crate's uncompressed form,
+ *     /root/reference/src/utils.rs:182-194); a G2 point is x.re||x.im||y.re||y.im (128 B, :162-179).  The point
+ *     at infinity, which the crate cannot serialise (/root/reference/src/utils.rs:86), is all-zero bytes.
+ *   - Per-item results are status bytes: one code per variant of the crate's Error enum
+ *     (/root/reference/src/error.rs:6-29), 0 = Ok(()).  A failed verification is BN254_VERIFICATION_FAILED,
+ *     exactly as Err(Error::VerificationFailed) at /root/reference/src/ecdsa.rs:62.
+ *   - Functions return 0 on success or a negative BN254_E_* engine error (CUDA failure, bad argument); the
+ *     message is available from bn254_last_error().  There is no CPU fallback: without a CUDA device
+ *     bn254_ctx_create fails.
+ *   - Entry points without a suffix take HOST buffers and include the host<->device copies; the *_dev variants
+ *     take DEVICE pointers (4-byte aligned), enqueue on the context's stream and return without synchronising
+ *     (call bn254_sync).  A context is bound to one GPU; calls on one context must not overlap.
+ */
+#ifndef BN254_B200_H
+#define BN254_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* per-item status = Error variant (/root/reference/src/error.rs:6-29) */
+enum {
+  BN254_OK = 0,
+  BN254_HASH_TO_POINT_ERROR = 1,
+  BN254_INDEX_OUT_OF_BOUNDS = 2,
+  BN254_INVALID_ENCODING = 3,
+  BN254_INVALID_GROUP_POINT = 4,
+  BN254_INVALID_LENGTH = 5,
+  BN254_NOT_MEMBER_ERROR = 6,
+  BN254_TO_AFFINE_CONVERSION = 7,
+  BN254_POINT_IN_JACOBIAN = 8,
+  BN254_VERIFICATION_FAILED = 9,
+  BN254_SERIALIZATION_ERROR = 10,
+  BN254_HEX_DECODE_FAILED = 11
+};
+
+/* engine-level errors (function return values) */
+enum { BN254_E_CUDA = -1, BN254_E_ARG = -2, BN254_E_NOMEM = -3 };
+
+typedef struct bn254_ctx bn254_ctx;
+
+/* lifecycle: one context per GPU; owns a stream, the -G2 line table, comb tables and the workspace */
+int bn254_ctx_create(int device, bn254_ctx** out);
+void bn254_ctx_destroy(bn254_ctx* ctx);
+const char* bn254_last_error(bn254_ctx* ctx); /* ctx may be NULL: error of the last failed create */
+int bn254_sync(bn254_ctx* ctx);
+void* bn254_stream(bn254_ctx* ctx);            /* the cudaStream_t used by every launch of this context */
+int bn254_sm_count(bn254_ctx* ctx);
+uint64_t bn254_launch_count(bn254_ctx* ctx);   /* kernels launched by this context so far */
+
+/* hash_to_try_and_increment (/root/reference/src/hash.rs:29-63): n messages of msg_len bytes each -> G1 */
+int bn254_hash_to_g1_batch(bn254_ctx*, const uint8_t* msgs, size_t msg_len, size_t n, uint8_t* g1_out, uint8_t* status);
+int bn254_hash_to_g1_batch_dev(bn254_ctx*, const uint8_t* msgs, size_t msg_len, size_t n, uint8_t* g1_out, uint8_t* status);
+/* ragged messages: message i = msgs[offsets[i] .. offsets[i+1])  (offsets has n+1 entries) */
+int bn254_hash_to_g1_var(bn254_ctx*, const uint8_t* msgs, const uint64_t* offsets, size_t n, uint8_t* g1_out, uint8_t* status,
+                         uint8_t* tries_out /* optional: accepted counter per message */);
+
+/* ECDSA::sign (/root/reference/src/ecdsa.rs:26-35): sig_i = H(msg_i) * sk_i ; sk is any 32 bytes, reduced mod r
+ * like Fr::from_slice (/root/reference/src/types.rs:37) */
+int bn254_sign_batch(bn254_ctx*, const uint8_t* msgs, size_t msg_len, const uint8_t* sks, size_t n, uint8_t* sigs, uint8_t* status);
+int bn254_sign_batch_dev(bn254_ctx*, const uint8_t* msgs, size_t msg_len, const uint8_t* sks, size_t n, uint8_t* sigs, uint8_t* status);
+
+/* ECDSA::verify (/root/reference/src/ecdsa.rs:49-64): status_i = verdict of e(H(msg_i), pk_i) * e(sig_i, -G2) == 1 */
+int bn254_verify_batch(bn254_ctx*, const uint8_t* msgs, size_t msg_len, const uint8_t* sigs, const uint8_t* pks, size_t n, uint8_t* status);
+int bn254_verify_batch_dev(bn254_ctx*, const uint8_t* msgs, size_t msg_len, const uint8_t* sigs, const uint8_t* pks, size_t n, uint8_t* status);
+
+/* check_public_keys (/root/reference/src/ecdsa.rs:78-93): e(G1, pk_g2_i) * e(pk_g1_i, -G2) == 1 */
+int bn254_check_public_keys_batch(bn254_ctx*, const uint8_t* pk_g2, const uint8_t* pk_g1, size_t n, uint8_t* status);
+
+/* bn::pairing_batch(...) == Gt::one() for n independent products of k pairs each (pairs with an infinity are skipped) */
+int bn254_pairing_check_batch(bn254_ctx*, const uint8_t* g1s, const uint8_t* g2s, size_t k, size_t n, uint8_t* status);
+
+/* Add / Sub / Neg folds (/root/reference/src/types.rs:126-148,196-218,264-286): out = sum of n points
+ * (optionally sum of (-1)^neg[i] * P_i when neg != NULL).  *status = first decode error or 0; an infinite sum is all-zero. */
+int bn254_g1_sum(bn254_ctx*, const uint8_t* pts, const uint8_t* neg, size_t n, uint8_t* out64, uint8_t* status);
+int bn254_g2_sum(bn254_ctx*, const uint8_t* pts, const uint8_t* neg, size_t n, uint8_t* out128, uint8_t* status);
+int bn254_g1_sum_dev(bn254_ctx*, const uint8_t* pts, const uint8_t* neg, size_t n, uint8_t* out64, uint8_t* status);
+int bn254_g2_sum_dev(bn254_ctx*, const uint8_t* pts, const uint8_t* neg, size_t n, uint8_t* out128, uint8_t* status);
+
+/* PublicKey::from_private_key / PublicKeyG1::from_private_key (/root/reference/src/types.rs:85-87,155-157) */
+int bn254_derive_pk_g2_batch(bn254_ctx*, const uint8_t* sks, size_t n, uint8_t* out128);
+int bn254_derive_pk_g1_batch(bn254_ctx*, const uint8_t* sks, size_t n, uint8_t* out64);
+
+/* generic G1 / G2 scalar multiplication by a 256-bit big-endian integer (bn256.json `mul` semantics) */
+int bn254_g1_mul_batch(bn254_ctx*, const uint8_t* pts, const uint8_t* scalars, size_t n, uint8_t* out64, uint8_t* status);
+int bn254_g2_mul_batch(bn254_ctx*, const uint8_t* pts, const uint8_t* scalars, size_t n, uint8_t* out128, uint8_t* status);
+
+/* codecs (/root/reference/src/utils.rs:84-194, bn::G1/G2::from_compressed): 33-byte G1 / 65-byte G2 compressed forms */
+int bn254_g1_compress_batch(bn254_ctx*, const uint8_t* raw64, size_t n, uint8_t* out33, uint8_t* status);
+int bn254_g1_decompress_batch(bn254_ctx*, const uint8_t* in33, size_t n, uint8_t* out64, uint8_t* status);
+int bn254_g2_compress_batch(bn254_ctx*, const uint8_t* raw128, size_t n, uint8_t* out65, uint8_t* status);
+int bn254_g2_decompress_batch(bn254_ctx*, const uint8_t* in65, size_t n, uint8_t* out128, uint8_t* status);
+/* from_uncompressed validation (/root/reference/src/utils.rs:107-127): membership, curve, and for G2 the r-torsion check */
+int bn254_g1_validate_batch(bn254_ctx*, const uint8_t* raw64, size_t n, uint8_t* status);
+int bn254_g2_validate_batch(bn254_ctx*, const uint8_t* raw128, size_t n, uint8_t* status);
+
+/* same-message aggregate verify (the flow of /root/reference/examples/bn254.rs:25-32): sum n sigs in G1 and n pks in G2,
+ * then one verify of (msg, sum_sig, sum_pk) */
+int bn254_aggregate_verify_same_msg(bn254_ctx*, const uint8_t* msg, size_t msg_len, const uint8_t* sigs, const uint8_t* pks, size_t n,
+                                    uint8_t* status);
+/* distinct-message aggregate verify: prod_i e(H(msg_i), pk_i) * e(agg_sig, -G2) == 1, one shared final exponentiation */
+int bn254_aggregate_verify_distinct(bn254_ctx*, const uint8_t* msgs, size_t msg_len, const uint8_t* pks, size_t n, const uint8_t* agg_sig,
+                                    uint8_t* status);
+/* multi-GPU building blocks of the above: each GPU reduces its slice to one Fq12 Miller product (12 x 32 B big-endian,
+ * tower order c0.c0.re .. c1.c2.im), the partials are exchanged (all-gather) and one rank finishes */
+int bn254_miller_partial_distinct(bn254_ctx*, const uint8_t* msgs, size_t msg_len, const uint8_t* pks, size_t n, uint8_t* f_out384,
+                                  uint8_t* status);
+int bn254_miller_partial_distinct_dev(bn254_ctx*, const uint8_t* msgs, size_t msg_len, const uint8_t* pks, size_t n, uint8_t* f_out384,
+                                      uint8_t* status);
+int bn254_finish_distinct(bn254_ctx*, const uint8_t* partials384, size_t n_partials, const uint8_t* agg_sig, uint8_t* status);
+
+/* building blocks exposed for parity tests and profiling of the two pairing phases */
+int bn254_miller_loop_batch(bn254_ctx*, const uint8_t* g1s, const uint8_t* g2s, size_t k, size_t n, uint8_t* f_out384, uint8_t* status);
+int bn254_final_exp_batch(bn254_ctx*, const uint8_t* f_in384, size_t n, uint8_t* gt_out384, uint8_t* status);
+/* Fq self-test hook: op 0 mul, 1 add, 2 sub, 3 inv, 4 sqrt (status 6 for a non-residue), 5 mul (portable cross-check variant) */
+int bn254_fq_op_batch(bn254_ctx*, int op, const uint8_t* a32, const uint8_t* b32, size_t n, uint8_t* out32, uint8_t* status);
+/* Fq12 self-test hook: op 0 mul, 1 sqr, 2 inv, 3 cyclotomic sqr, 4..6 frobenius 1..3, 7 conj */
+int bn254_fq12_op_batch(bn254_ctx*, int op, const uint8_t* a384, const uint8_t* b384, size_t n, uint8_t* out384, uint8_t* status);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BN254_B200_H */

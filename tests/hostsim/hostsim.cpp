@@ -1,0 +1,160 @@
+// hostsim.cpp -- compiles the engine's per-item device code (bn254_b200/csrc/*.cuh) with g++ for the CPU.
+// TEST INFRASTRUCTURE ONLY: lets `pytest -m "not gpu"` check the control logic of the kernels (tower formulas,
+// Miller schedule, final-exponentiation chain, hash loop, codecs) against the oracle on a machine without a GPU.
+// It is never loaded by the product library or by bench.py; the PTX Montgomery product is device-only and is
+// checked on the GPU by the `-m gpu` tests.
+#include <cstddef>
+#include <cstdint>
+#include <cstring>
+#include "../../bn254_b200/csrc/items.cuh"
+
+using namespace bn;
+#define API extern "C" __attribute__((visibility("default")))
+
+static line_t g_lines[K_N_LINES];
+static bool g_init = false;
+static void ensure_init() {
+  if (g_init) return;
+  fq2 gx = fq2_from_limbs(K_G2_GEN_X), gy = fq2_neg(fq2_from_limbs(K_G2_GEN_Y));
+  g2_precompute_lines(g_lines, gx, gy);
+  g_init = true;
+}
+
+API int hs_hash_to_g1(const uint8_t* msg, size_t len, uint8_t* out, int* ctr) {
+  g1aff h;
+  int st = hash_to_g1(&h.x, &h.y, msg, len, ctr);
+  if (st) { memset(out, 0, 64); return st; }
+  fq_to_be(out, h.x); fq_to_be(out + 32, h.y);
+  return 0;
+}
+API int hs_sign(const uint8_t* msg, size_t len, const uint8_t* sk, uint8_t* sig) {
+  g1aff h;
+  int st = hash_to_g1(&h.x, &h.y, msg, len, nullptr);
+  if (st) { memset(sig, 0, 64); return st; }
+  item_sign(sig, &h, sk);
+  return 0;
+}
+API int hs_verify(const uint8_t* msg, size_t len, const uint8_t* sig, const uint8_t* pk) {
+  ensure_init();
+  g1aff h;
+  int st = hash_to_g1(&h.x, &h.y, msg, len, nullptr);
+  if (st) return st;
+  fq12 f;
+  st = item_verify_miller(&f, &h, sig, pk, g_lines);
+  if (st) return st;
+  return item_final_exp_is_one(&f);
+}
+API int hs_check_public_keys(const uint8_t* pk_g2, const uint8_t* pk_g1) {
+  ensure_init();
+  g1aff h;
+  h.x = fq_from_limbs(K_G1_GEN_X); h.y = fq_from_limbs(K_G1_GEN_Y);
+  fq12 f;
+  int st = item_verify_miller(&f, &h, pk_g1, pk_g2, g_lines);
+  if (st) return st;
+  return item_final_exp_is_one(&f);
+}
+API int hs_verify_miller(const uint8_t* msg, size_t len, const uint8_t* sig, const uint8_t* pk, uint8_t* f_out) {
+  ensure_init();
+  g1aff h;
+  int st = hash_to_g1(&h.x, &h.y, msg, len, nullptr);
+  if (st) return st;
+  fq12 f;
+  st = item_verify_miller(&f, &h, sig, pk, g_lines);
+  if (st) return st;
+  fq12_to_be(f_out, &f);
+  return 0;
+}
+API int hs_miller_product(const uint8_t* g1s, const uint8_t* g2s, size_t k, uint8_t* f_out) {
+  fq12 f;
+  int st = item_miller_pairs(&f, g1s, g2s, k);
+  if (st) return st;
+  fq12_to_be(f_out, &f);
+  return 0;
+}
+API int hs_pairing_check(const uint8_t* g1s, const uint8_t* g2s, size_t k) {
+  fq12 f;
+  int st = item_miller_pairs(&f, g1s, g2s, k);
+  if (st) return st;
+  return item_final_exp_is_one(&f);
+}
+API int hs_final_exp(const uint8_t* f_in, uint8_t* gt_out) {
+  fq12 f, gt;
+  if (!fq12_from_be(&f, f_in)) return ST_NOT_MEMBER;
+  if (!final_exponentiation(&gt, &f)) return ST_TO_AFFINE;
+  fq12_to_be(gt_out, &gt);
+  return 0;
+}
+API int hs_fq_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
+  fq x, y, r;
+  if (!fq_from_be(&x, a)) return ST_NOT_MEMBER;
+  if (op <= 2 && !fq_from_be(&y, b)) return ST_NOT_MEMBER;
+  if (op == 0) r = fq_mul(x, y);
+  else if (op == 1) r = fq_add(x, y);
+  else if (op == 2) r = fq_sub(x, y);
+  else if (op == 3) r = fq_inv(x);
+  else if (op == 4) { if (!fq_sqrt(&r, x)) return ST_NOT_MEMBER; }
+  else return ST_INVALID_ENCODING;
+  fq_to_be(out, r);
+  return 0;
+}
+API int hs_fq12_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
+  fq12 x, y, r;
+  if (!fq12_from_be(&x, a)) return ST_NOT_MEMBER;
+  if (op == 0) { if (!fq12_from_be(&y, b)) return ST_NOT_MEMBER; fq12_mul(&r, &x, &y); }
+  else if (op == 1) fq12_sqr(&r, &x);
+  else if (op == 2) fq12_inv(&r, &x);
+  else if (op == 3) fq12_cyclotomic_sqr(&r, &x);
+  else if (op >= 4 && op <= 6) fq12_frobenius(&r, &x, op - 3);
+  else if (op == 7) fq12_conj(&r, &x);
+  else return ST_INVALID_ENCODING;
+  fq12_to_be(out, &r);
+  return 0;
+}
+API int hs_g1_mul(const uint8_t* pt, const uint8_t* k, uint8_t* out) { return item_g1_mul(out, pt, k); }
+API int hs_g2_mul(const uint8_t* pt, const uint8_t* k, uint8_t* out) { return item_g2_mul(out, pt, k); }
+API int hs_g1_add(const uint8_t* a, const uint8_t* b, uint8_t* out) {
+  g1j p, q, r;
+  int st;
+  if ((st = g1_from_raw(&p, a)) || (st = g1_from_raw(&q, b))) return st;
+  pt_add(&r, &p, &q);
+  g1_to_raw(out, &r);
+  return 0;
+}
+API int hs_g1_madd(const uint8_t* a, const uint8_t* b, uint8_t* out) {  // b finite
+  g1j p, q, r;
+  int st;
+  if ((st = g1_from_raw(&p, a)) || (st = g1_from_raw(&q, b))) return st;
+  pt_madd(&r, &p, &q.x, &q.y);
+  g1_to_raw(out, &r);
+  return 0;
+}
+API int hs_g2_add(const uint8_t* a, const uint8_t* b, uint8_t* out) {
+  g2j p, q, r;
+  int st;
+  if ((st = g2_from_raw(&p, a)) || (st = g2_from_raw(&q, b))) return st;
+  pt_add(&r, &p, &q);
+  g2_to_raw(out, &r);
+  return 0;
+}
+API int hs_g2_madd(const uint8_t* a, const uint8_t* b, uint8_t* out) {
+  g2j p, q, r;
+  int st;
+  if ((st = g2_from_raw(&p, a)) || (st = g2_from_raw(&q, b))) return st;
+  pt_madd(&r, &p, &q.x, &q.y);
+  g2_to_raw(out, &r);
+  return 0;
+}
+API int hs_derive_pk_g1(const uint8_t* sk, uint8_t* out) { item_derive_pk_g1(out, sk); return 0; }
+API int hs_derive_pk_g2(const uint8_t* sk, uint8_t* out) { item_derive_pk_g2(out, sk); return 0; }
+API int hs_g1_compress(const uint8_t* raw, uint8_t* out) { return item_g1_compress(out, raw); }
+API int hs_g1_decompress(const uint8_t* in, size_t len, uint8_t* out) {
+  if (len != 33) { memset(out, 0, 64); return ST_INVALID_ENCODING; }
+  return item_g1_decompress(out, in);
+}
+API int hs_g2_compress(const uint8_t* raw, uint8_t* out) { return item_g2_compress(out, raw); }
+API int hs_g2_decompress(const uint8_t* in, size_t len, uint8_t* out) {
+  if (len != 65) { memset(out, 0, 128); return ST_INVALID_ENCODING; }
+  return item_g2_decompress(out, in);
+}
+API int hs_g1_validate(const uint8_t* raw, size_t len) { return len == 64 ? item_g1_validate(raw) : ST_INVALID_LENGTH; }
+API int hs_g2_validate(const uint8_t* raw, size_t len) { return len == 128 ? item_g2_validate(raw) : ST_INVALID_LENGTH; }

@@ -1,0 +1,216 @@
+"""CPU check of the engine's per-item device code (compiled by g++ in tests/hostsim) against the oracle:
+tower formulas, Miller schedule with the -G2 line table, final-exponentiation chain, hash loop, group law
+and codecs.  The GPU tests repeat these through the real kernels; this catches logic errors without a GPU."""
+import ctypes
+import json
+import os
+import random
+import subprocess
+
+import pytest
+
+import oracle_lib as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HS_DIR = os.path.join(ROOT, "tests", "hostsim")
+G = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_vectors.json")))
+H = bytes.fromhex
+Q = 0x30644E72E131A029B85045B68181585D97816A916871CA8D3C208C16D87CFD47
+R = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+G1_GEN = (1).to_bytes(32, "big") + (2).to_bytes(32, "big")
+
+
+@pytest.fixture(scope="module")
+def hs():
+    subprocess.check_call(["make", "-C", HS_DIR], stdout=subprocess.DEVNULL)
+    return ctypes.CDLL(os.path.join(HS_DIR, "libhostsim.so"))
+
+
+def buf(n):
+    return ctypes.create_string_buffer(n)
+
+
+def be(x, n=32):
+    return x.to_bytes(n, "big")
+
+
+def test_fq_ops(hs):
+    rng = random.Random(1)
+    cases = [(0, 0), (1, 1), (Q - 1, Q - 1), (Q - 1, 1), (0, Q - 1)] + [(rng.randrange(Q), rng.randrange(Q)) for _ in range(300)]
+    for a, b in cases:
+        for op in (0, 1, 2):
+            out = buf(32)
+            assert hs.hs_fq_op(op, be(a), be(b), out) == 0
+            assert out.raw == O.fq_op(op, be(a), be(b))[1], (op, a, b)
+    for a, _ in cases[:40]:
+        for op in (3, 4):
+            out = buf(32)
+            st = hs.hs_fq_op(op, be(a), be(0), out)
+            est, e = O.fq_op(op, be(a))
+            assert st == est and (st != 0 or out.raw == e)
+
+
+def rand_fq12(rng):
+    return b"".join(be(rng.randrange(Q)) for _ in range(12))
+
+
+def test_fq12_ops(hs):
+    rng = random.Random(2)
+    for _ in range(10):
+        a, b = rand_fq12(rng), rand_fq12(rng)
+        for op in range(8):
+            out = buf(384)
+            assert hs.hs_fq12_op(op, a, b, out) == 0
+            assert out.raw == O.fq12_op(op, a, b)[1], op
+
+
+def test_hash_kats_and_random(hs):
+    for v in G["hash_to_g1"]:
+        out, ctr = buf(64), ctypes.c_int(-1)
+        assert hs.hs_hash_to_g1(H(v["msg"]), len(H(v["msg"])), out, ctypes.byref(ctr)) == 0
+        assert O.g1_compress(out.raw) == (0, H(v["compressed"]))
+    rng = random.Random(3)
+    for _ in range(300):
+        msg = rng.randbytes(rng.choice([0, 1, 3, 31, 32, 33, 54, 55, 56, 62, 63, 64, 65, 118, 119, 120, 127, 128, 300]))
+        out, ctr = buf(64), ctypes.c_int(-1)
+        st = hs.hs_hash_to_g1(msg, len(msg), out, ctypes.byref(ctr))
+        est, e, ectr = O.hash_to_g1(msg)
+        assert (st, out.raw, ctr.value) == (est, e, ectr)
+
+
+def test_sign_kat_and_group_vectors(hs):
+    for v in G["sign"]:
+        sig = buf(64)
+        assert hs.hs_sign(H(v["msg"]), len(H(v["msg"])), H(v["sk"]), sig) == 0
+        assert O.g1_compress(sig.raw) == (0, H(v["sig_compressed"]))
+    for v in G["sk_to_pk_g2"]:
+        out = buf(128)
+        hs.hs_derive_pk_g2(H(v["sk"]), out)
+        assert out.raw == H(v["pk_uncompressed"])
+    for v in G["bn256_json"]["add"]:
+        out = buf(64)
+        assert hs.hs_g1_add(H(v["x1"]) + H(v["y1"]), H(v["x2"]) + H(v["y2"]), out) == 0
+        assert out.raw == H(v["result"])
+        if any(H(v["x2"]) + H(v["y2"])):
+            assert hs.hs_g1_madd(H(v["x1"]) + H(v["y1"]), H(v["x2"]) + H(v["y2"]), out) == 0
+            assert out.raw == H(v["result"])
+    for v in G["bn256_json"]["mul"]:
+        out = buf(64)
+        assert hs.hs_g1_mul(H(v["x"]) + H(v["y"]), H(v["scalar"]), out) == 0
+        assert out.raw == H(v["result"])
+    for sk in G["example"]["sks"]:  # keys > r
+        o1, o2 = buf(64), buf(128)
+        hs.hs_derive_pk_g1(H(sk), o1)
+        hs.hs_derive_pk_g2(H(sk), o2)
+        assert o1.raw == O.derive_pk_g1(H(sk))[1] and o2.raw == O.derive_pk_g2(H(sk))[1]
+
+
+def test_g2_group(hs):
+    rng = random.Random(4)
+    g2 = O.derive_pk_g2(be(1))[1]
+    pts = [O.derive_pk_g2(be(rng.randrange(1, R)))[1] for _ in range(4)] + [bytes(128), g2]
+    for a in pts:
+        for b in pts:
+            out = buf(128)
+            assert hs.hs_g2_add(a, b, out) == 0 and out.raw == O.g2_add(a, b)[1]
+            if any(b):
+                assert hs.hs_g2_madd(a, b, out) == 0 and out.raw == O.g2_add(a, b)[1]
+    neg = O.g2_neg(pts[0])[1]
+    out = buf(128)
+    assert hs.hs_g2_add(pts[0], neg, out) == 0 and out.raw == bytes(128)
+    assert hs.hs_g2_madd(pts[0], neg, out) == 0 and out.raw == bytes(128)
+    k = be(rng.randrange(1 << 256))
+    assert hs.hs_g2_mul(pts[1], k, out) == 0 and out.raw == O.g2_mul(pts[1], k)[1]
+
+
+def test_verify_and_miller(hs):
+    rng = random.Random(5)
+    for t in range(6):
+        sk = be(rng.randrange(1, R))
+        msg = rng.randbytes(32)
+        sig = O.sign(msg, sk)[1]
+        pk = O.derive_pk_g2(sk)[1]
+        assert hs.hs_verify(msg, len(msg), sig, pk) == 0
+        # Miller product is bit-identical to the oracle's (same field values, canonical form)
+        h = O.hash_to_g1(msg)[1]
+        neg_g2 = O.g2_neg(O.derive_pk_g2(be(1))[1])[1]
+        f = buf(384)
+        assert hs.hs_verify_miller(msg, len(msg), sig, pk, f) == 0
+        assert f.raw == O.miller_product(h + sig, pk + neg_g2, 2)[1]
+        gt = buf(384)
+        assert hs.hs_final_exp(f.raw, gt) == 0 and gt.raw == O.final_exp(f.raw)[1]
+        # adversarial
+        bad = O.g1_add(sig, G1_GEN)[1]
+        assert hs.hs_verify(msg, len(msg), bad, pk) == O.VERIFICATION_FAILED == O.verify(msg, bad, pk)
+        assert hs.hs_verify(msg + b"x", len(msg) + 1, sig, pk) == O.VERIFICATION_FAILED
+        assert hs.hs_verify(msg, len(msg), O.g1_neg(sig)[1], pk) == O.VERIFICATION_FAILED
+    assert hs.hs_verify(b"m", 1, bytes(64), bytes(128)) == 0 == O.verify(b"m", bytes(64), bytes(128))
+    assert hs.hs_verify(b"m", 1, bytes(64), pk) == O.VERIFICATION_FAILED
+    assert hs.hs_verify(b"m", 1, sig, bytes(128)) == O.VERIFICATION_FAILED == O.verify(b"m", sig, bytes(128))
+    assert hs.hs_verify(b"m", 1, be(1) + be(3), pk) == O.INVALID_GROUP_POINT == O.verify(b"m", be(1) + be(3), pk)
+    assert hs.hs_verify(b"m", 1, be(Q) + be(3), pk) == O.NOT_MEMBER == O.verify(b"m", be(Q) + be(3), pk)
+    for v in G["check_public_keys_ok"]:
+        assert hs.hs_check_public_keys(O.derive_pk_g2(H(v["sk"]))[1], O.derive_pk_g1(H(v["sk"]))[1]) == 0
+    for v in G["check_public_keys_fail"]:
+        assert hs.hs_check_public_keys(O.derive_pk_g2(H(v["sk_g2"]))[1], O.derive_pk_g1(H(v["sk_g1"]))[1]) == O.VERIFICATION_FAILED
+
+
+def test_pairing_pairs(hs):
+    rng = random.Random(6)
+    a, b = rng.randrange(1, R), rng.randrange(1, R)
+    pa = O.derive_pk_g1(be(a))[1]
+    qb = O.derive_pk_g2(be(b))[1]
+    pab = O.derive_pk_g1(be(a * b % R))[1]
+    neg_g2 = O.g2_neg(O.derive_pk_g2(be(1))[1])[1]
+    g1s, g2s = pa + pab + bytes(64), qb + neg_g2 + qb
+    assert hs.hs_pairing_check(g1s, g2s, 3) == 0 == O.pairing_check(g1s, g2s, 3)[0]
+    f = buf(384)
+    assert hs.hs_miller_product(g1s, g2s, 3, f) == 0 and f.raw == O.miller_product(g1s, g2s, 3)[1]
+    assert hs.hs_pairing_check(pa + pa, qb + neg_g2, 2) == O.VERIFICATION_FAILED
+    assert hs.hs_pairing_check(b"", b"", 0) == 0
+
+
+def test_codecs(hs):
+    rng = random.Random(8)
+    for v in G["g2_compressed_roundtrip"]:
+        out = buf(128)
+        assert hs.hs_g2_decompress(H(v["compressed"]), 65, out) == 0
+        assert out.raw == O.g2_decompress(H(v["compressed"]))[1]
+        c = buf(65)
+        assert hs.hs_g2_compress(out.raw, c) == 0 and c.raw == H(v["compressed"])
+    for _ in range(3):
+        pk = O.derive_pk_g2(be(rng.randrange(1, R)))[1]
+        c = buf(65)
+        assert hs.hs_g2_compress(pk, c) == 0 and c.raw == O.g2_compress(pk)[1]
+        out = buf(128)
+        assert hs.hs_g2_decompress(c.raw, 65, out) == 0 and out.raw == pk
+        assert hs.hs_g2_validate(pk, 128) == 0
+        bad = bytes([c.raw[0] ^ 1]) + c.raw[1:]
+        assert hs.hs_g2_decompress(bad, 65, out) == 0 and out.raw == O.g2_neg(pk)[1]
+        assert hs.hs_g2_decompress(b"\x0c" + c.raw[1:], 65, out) == O.INVALID_ENCODING
+    for _ in range(20):
+        p = O.derive_pk_g1(be(rng.randrange(1, R)))[1]
+        c = buf(33)
+        assert hs.hs_g1_compress(p, c) == 0 and c.raw == O.g1_compress(p)[1]
+        out = buf(64)
+        assert hs.hs_g1_decompress(c.raw, 33, out) == 0 and out.raw == p
+        x = be(rng.randrange(Q))
+        st = hs.hs_g1_decompress(b"\x03" + x, 33, out)
+        est, e = O.g1_decompress(b"\x03" + x)
+        assert st == est and out.raw == e
+    assert hs.hs_g1_decompress(b"\x02" + be(Q), 33, buf(64)) == O.NOT_MEMBER
+    assert hs.hs_g1_decompress(b"\x04" + be(1), 33, buf(64)) == O.INVALID_ENCODING
+    assert hs.hs_g1_validate(be(1) + be(3), 64) == O.INVALID_GROUP_POINT
+    assert hs.hs_g1_compress(bytes(64), buf(33)) == O.POINT_IN_JACOBIAN
+    # twist point outside the r-torsion
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle as P
+    x = 1
+    while True:
+        y = P.f2_sqrt(P.f2_add(P.f2_mul(P.f2_mul((x, 0), (x, 0)), (x, 0)), P.B2))
+        if y is not None and not P.g2_in_subgroup(((x, 0), y)):
+            break
+        x += 1
+    raw = be(x) + be(0) + be(y[0]) + be(y[1])
+    assert hs.hs_g2_validate(raw, 128) == O.INVALID_GROUP_POINT == O.g2_validate_uncompressed(raw)
