@@ -1,0 +1,272 @@
+#!/usr/bin/env python3
+"""bench.py -- BN254 batch-verify throughput on B200 (BASELINE.json configs[1]) and the CPU reference arm.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl engine|reference] [--n ITEMS]
+
+A step = one pass of ECDSA::verify over a batch of 2^20 independent (32-byte msg, sig, pk) triples per GPU
+(weak scaling: every rank verifies its own 2^20 triples, no data-path collective).  Prints ONE JSON line:
+  value       verifies/s, whole job, inputs resident in HBM when the timed region starts (CUDA events on the
+              engine's stream, max over ranks)
+  e2e         the same metric through the public host-buffer entry point (bn254_verify_batch via
+              bn254_b200.engine.verify_batch): pinned host inputs, H2D + kernels + D2H of the verdicts timed
+  roofline    INT32 multiply-pipe roofline of the dominant phase (Miller loop + final exponentiation):
+              achieved = algorithmic IMAD32 (264 per Fq product) per second, peak = the IMAD issue
+              rate measured live by tools/microbench.bin on this GPU (the path is integer-issue bound: a verify
+              reads 224 B and does ~5.8 M IMAD32-equivalents, so neither HBM nor tensor peak applies)
+  cpu_baseline  the oracle (C restatement of the dependency's algorithms) timed on the host cores, bounded sample
+`--impl reference` times the CPU path alone (the Rust crate cannot be built here: no cargo/rustc; oracle/ port).
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+M_VERIFY = 21885        # Fq-mul equivalents per verify
+M_PAIRING_PART = 21111  # Miller (2-pair, shared squarings) + final exponentiation share of a verify
+IMAD_PER_M = 264
+METRIC = "bn254_verifies_per_sec"
+UNIT = "verifies/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--n", type=int, default=1 << 20, help="triples per GPU per step")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="verifies in the CPU baseline sample (0 = auto)")
+    return ap.parse_args()
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+
+    def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            names = {
+                pynvml.nvmlClocksEventReasonSwPowerCap if hasattr(pynvml, "nvmlClocksEventReasonSwPowerCap") else 0x4: "sw_power_cap",
+                0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown",
+            }
+            while not self.stop_flag:
+                self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                try:
+                    r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.1)
+        except Exception as e:  # no NVML: report that instead of inventing clocks
+            self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
+
+    def result(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def cpu_baseline(n_sample, msgs, sigs, pks, threads):
+    """Oracle verify on the host cores over the first n_sample triples of the workload (the checker timed, never shipped)."""
+    import oracle_lib as O
+    O.verify_batch(msgs[:32 * 8], 32, sigs[:64 * 8], pks[:128 * 8], 8, threads)  # warm (one-time init)
+    t = time.perf_counter()
+    st = O.verify_batch(msgs[:32 * n_sample], 32, sigs[:64 * n_sample], pks[:128 * n_sample], n_sample, threads)
+    dt = time.perf_counter() - t
+    return n_sample / dt, dt, st
+
+
+def run_reference(args):
+    """CPU arm: the reference's own CPU implementation cannot be built here (Rust; dependency not vendored), so this
+    times the oracle port with every host thread, each step a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle_lib as O
+    import synth
+    threads = os.cpu_count() or 1
+    n = args.cpu_sample or max(256, 128 * threads)
+    msgs, sks = synth.messages(n, 32, seed=1), synth.secret_keys(n, seed=2)
+    sigs, st = O.sign_batch(msgs, 32, sks, n, threads)
+    pks = O.derive_pk_g2_batch(sks, n, threads)
+    for _ in range(max(1, min(args.warmup, 1))):
+        O.verify_batch(msgs, 32, sigs, pks, min(n, 64), threads)
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        out = O.verify_batch(msgs, 32, sigs, pks, n, threads)
+    dt = time.perf_counter() - t
+    assert out == bytes(n)
+    v = n * args.steps / dt
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+        "data": "synthetic", "config": {"workload": "batch verify 2^20 independent (32-byte msg, sig, pk) triples", "sample_per_step": n},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "%d verifies per step x %d steps, oracle/bn254_oracle.c on %d threads" % (n, args.steps, threads)},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def imad_peak():
+    """Measured INT32 IMAD issue rate of this GPU (ops/s) from tools/microbench.bin; None if it cannot run."""
+    exe = os.path.join(ROOT, "tools", "microbench.bin")
+    try:
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=300, check=True).stdout.strip().splitlines()[-1]
+        return json.loads(out)
+    except Exception as e:
+        return {"error": "%s: %s" % (type(e).__name__, e)}
+
+
+def run_engine(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import bn254_b200
+    from bn254_b200 import engine as E
+    from bn254_b200._native import S
+    import synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = E.context(local)
+    n = args.n
+
+    # ---- synthetic workload: seeded messages and keys; signatures and keys made by the engine
+    seed = 1 + 1000 * rank
+    msgs, sks = synth.messages(n, 32, seed=seed), synth.secret_keys(n, seed=seed + 1)
+    sigs, st = E.sign_batch(msgs, 32, sks, ctx=ctx)
+    assert not any(st)
+    pks = E.derive_pk_g2_batch(sks, ctx=ctx)
+
+    def dev(b):
+        return torch.frombuffer(bytearray(b), dtype=torch.uint8).cuda()
+
+    def pinned(b):
+        return torch.frombuffer(bytearray(b), dtype=torch.uint8).pin_memory()
+
+    d_msgs, d_sigs, d_pks = dev(msgs), dev(sigs), dev(pks)
+    d_st = torch.empty(n, dtype=torch.uint8, device="cuda")
+    h_msgs, h_sigs, h_pks = pinned(msgs), pinned(sigs), pinned(pks)
+    h_st = torch.empty(n, dtype=torch.uint8).pin_memory()
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
+    torch.cuda.synchronize()
+
+    def step_dev():
+        ctx.call("bn254_verify_batch_dev", d_msgs, S(32), d_sigs, d_pks, S(n), d_st)
+
+    def step_e2e():
+        ctx.call("bn254_verify_batch", h_msgs, S(32), h_sigs, h_pks, S(n), h_st)
+
+    def barrier():
+        torch.cuda.synchronize()
+        ctx.sync()
+        if world > 1:
+            dist.barrier()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        ctx.sync()
+        e1.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        barrier()
+        return ms
+
+    for _ in range(args.warmup):
+        step_dev()
+    barrier()
+    assert bytes(d_st.cpu().numpy().tobytes()) == bytes(n), "engine rejected valid signatures"
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = ctx.launch_count
+    ms_total = timed(step_dev, args.steps)
+    launches = ctx.launch_count - launches0
+    # per-phase device time of the same pipeline (events between its kernels), one extra profiled step
+    phase = (ctypes.c_float * 3)()
+    ctx.call("bn254_set_profiling", bn254_b200._native.I(1))
+    step_dev()
+    ctx.call("bn254_phase_ms", phase)
+    ctx.call("bn254_set_profiling", bn254_b200._native.I(0))
+    # end to end through the host-buffer entry point
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    assert bytes(h_st.numpy().tobytes()) == bytes(n)
+
+    value = world * n * args.steps / (ms_total * 1e-3)
+    e2e = world * n * args.steps / (ms_e2e * 1e-3)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cal = imad_peak()
+    peak = cal.get("imad_lo", {}).get("gops") if isinstance(cal, dict) else None
+    pairing_ms = phase[1] + phase[2]
+    achieved = (n * M_PAIRING_PART * IMAD_PER_M / (pairing_ms * 1e-3) / 1e9) if pairing_ms > 0 else None
+    roof = {
+        "bound": "int32_imad", "kernel": "k_verify_miller + k_final_exp_check", "achieved": achieved, "peak": peak, "unit": "GIMAD32/s",
+        "frac": (achieved / peak if achieved and peak else None), "traffic": None,
+        "peak_source": "tools/microbench.bin mad.lo.u32 chain measured in this run (MEASURED_PEAKS.json has no int32 figure)",
+        "phase_ms": {"hash_to_g1": phase[0], "miller": phase[1], "final_exp": phase[2]},
+        "calibration": cal,
+    }
+    threads = os.cpu_count() or 1
+    n_cpu = args.cpu_sample or max(256, 64 * threads)
+    cpu_v, cpu_dt, cpu_st = cpu_baseline(n_cpu, msgs, sigs, pks, threads)
+    assert cpu_st == bytes(n_cpu)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+        "data": "synthetic",
+        "config": {"workload": "batch verify 2^20 independent (32-byte msg, sig, pk) triples per GPU (BASELINE configs[1])",
+                   "triples_per_gpu": n, "msg_len": 32, "l2": "inputs+workspace (%.0f MB) larger than L2" % ((224 + 448) * n / 1e6),
+                   "pairings_per_sec": value * 2},
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 224 * n, "d2h_bytes_per_step": n, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches, "clocks": sampler.result(), "roofline": roof,
+        "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "first %d triples of the workload, oracle/bn254_oracle.c on %d threads, %.1f s" % (n_cpu, threads, cpu_dt)},
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_engine(a)

@@ -1,0 +1,965 @@
+// bn254_b200.cu -- CUDA kernels (sm_100a) and the C ABI of the BN254 batch engine (include/bn254_b200.h).
+//
+// One thread owns one item (message / signature / key / pairing product).  The path is integer-pipe bound
+// (IMAD.WIDE carry chains), not HBM or tensor bound: a verify reads 224 B and issues ~3 M multiply-adds.
+// Phases are separate kernels so that the divergent try-and-increment hash, the uniform Miller loop and the
+// uniform final exponentiation each run with their own register budget and can be profiled on their own:
+//     k_hash_to_g1 -> k_verify_miller -> k_final_exp_check            (ECDSA::verify, /root/reference/src/ecdsa.rs:49-64)
+//     k_hash_to_g1 -> k_sign                                          (ECDSA::sign,   /root/reference/src/ecdsa.rs:26-35)
+//     k_sum_partial<F> -> k_sum_final<F>                              (Add/Sub/Neg folds, /root/reference/src/types.rs:126-286)
+//     k_hash_to_g1 -> k_distinct_partial -> k_fq12_prod_final -> k_distinct_finish   (multi-pairing, one final exponentiation)
+// There is no CPU fallback anywhere in this file: without a CUDA device bn254_ctx_create fails.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/bn254_b200.h"
+#include "items.cuh"
+
+using namespace bn;
+
+#define BN_BLOCK 128
+#define BN_PROD_BLOCK 64
+
+// ------------------------------------------------------------------------------------------------ kernels
+__global__ void k_init_lines(line_t* out) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    fq2 gx = fq2_from_limbs(K_G2_GEN_X), gy = fq2_neg(fq2_from_limbs(K_G2_GEN_Y));
+    g2_precompute_lines(out, gx, gy);
+  }
+}
+
+// hash_to_try_and_increment for message i = msgs[i*msg_len ..] (offsets == NULL) or msgs[offsets[i] .. offsets[i+1])
+__global__ void __launch_bounds__(BN_BLOCK) k_hash_to_g1(const uint8_t* __restrict__ msgs, size_t msg_len, const uint64_t* __restrict__ offsets,
+                                                         size_t n, g1aff* __restrict__ H, uint8_t* __restrict__ status,
+                                                         uint8_t* __restrict__ tries) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint8_t* m = offsets ? msgs + offsets[i] : msgs + i * msg_len;
+  uint64_t len = offsets ? offsets[i + 1] - offsets[i] : msg_len;
+  g1aff h;
+  int ctr = 0;
+  int st = hash_to_g1(&h.x, &h.y, m, len, &ctr);
+  if (st) {
+    h.x = fq_zero();
+    h.y = fq_zero();
+  }
+  H[i] = h;
+  status[i] = (uint8_t)st;
+  if (tries) tries[i] = (uint8_t)ctr;
+}
+
+__global__ void __launch_bounds__(BN_BLOCK) k_g1aff_to_raw(const g1aff* __restrict__ H, const uint8_t* __restrict__ status, size_t n,
+                                                           uint8_t* __restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (status[i]) {
+    for (int k = 0; k < 64; k++) out[64 * i + k] = 0;
+    return;
+  }
+  fq_to_be(out + 64 * i, H[i].x);
+  fq_to_be(out + 64 * i + 32, H[i].y);
+}
+
+__global__ void __launch_bounds__(BN_BLOCK) k_sign(const g1aff* __restrict__ H, const uint8_t* __restrict__ sks, size_t n,
+                                                   uint8_t* __restrict__ sigs, const uint8_t* __restrict__ status) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (status[i]) {
+    for (int k = 0; k < 64; k++) sigs[64 * i + k] = 0;
+    return;
+  }
+  g1aff h = H[i];
+  item_sign(sigs + 64 * i, &h, sks + 32 * i);
+}
+
+// H == NULL: the first G1 argument is the generator (check_public_keys, /root/reference/src/ecdsa.rs:78-93)
+__global__ void __launch_bounds__(BN_BLOCK) k_verify_miller(const g1aff* __restrict__ H, const uint8_t* __restrict__ sigs,
+                                                            const uint8_t* __restrict__ pks, size_t n, fq12* __restrict__ F,
+                                                            uint8_t* __restrict__ status, const line_t* __restrict__ lines) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (H && status[i]) return;  // hash error propagates (/root/reference/src/ecdsa.rs:53)
+  g1aff h;
+  if (H) {
+    h = H[i];
+  } else {
+    h.x = fq_from_limbs(K_G1_GEN_X);
+    h.y = fq_from_limbs(K_G1_GEN_Y);
+  }
+  fq12 f;
+  int st = item_verify_miller(&f, &h, sigs + 64 * i, pks + 128 * i, lines);
+  status[i] = (uint8_t)st;
+  if (!st) F[i] = f;
+}
+
+__global__ void __launch_bounds__(BN_BLOCK) k_final_exp_check(const fq12* __restrict__ F, size_t n, uint8_t* __restrict__ status) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (status[i]) return;
+  fq12 f = F[i];
+  status[i] = item_final_exp_is_one(&f);
+}
+
+__global__ void __launch_bounds__(BN_BLOCK) k_miller_pairs(const uint8_t* __restrict__ g1s, const uint8_t* __restrict__ g2s, size_t k, size_t n,
+                                                           fq12* __restrict__ F, uint8_t* __restrict__ status) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  fq12 f;
+  int st = item_miller_pairs(&f, g1s + 64 * k * i, g2s + 128 * k * i, k);
+  status[i] = (uint8_t)st;
+  if (!st) F[i] = f;
+}
+
+__global__ void __launch_bounds__(BN_BLOCK) k_fq12_to_be(const fq12* __restrict__ F, const uint8_t* __restrict__ status, size_t n,
+                                                         uint8_t* __restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (status && status[i]) {
+    for (int k = 0; k < 384; k++) out[384 * i + k] = 0;
+    return;
+  }
+  fq12 f = F[i];
+  fq12_to_be(out + 384 * i, &f);
+}
+
+__global__ void __launch_bounds__(BN_BLOCK) k_final_exp_bytes(const uint8_t* __restrict__ in, size_t n, uint8_t* __restrict__ out,
+                                                              uint8_t* __restrict__ status) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  fq12 f, gt;
+  int st = ST_OK;
+  if (!fq12_from_be(&f, in + 384 * i)) st = ST_NOT_MEMBER;
+  else if (!final_exponentiation(&gt, &f)) st = ST_TO_AFFINE;
+  status[i] = (uint8_t)st;
+  if (st) {
+    for (int k = 0; k < 384; k++) out[384 * i + k] = 0;
+  } else {
+    fq12_to_be(out + 384 * i, &gt);
+  }
+}
+
+__global__ void __launch_bounds__(BN_BLOCK) k_fq_op(int op, const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, size_t n,
+                                                    uint8_t* __restrict__ out, uint8_t* __restrict__ status) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  fq x, y, r = fq_zero();
+  int st = ST_OK;
+  if (!fq_from_be(&x, a + 32 * i)) st = ST_NOT_MEMBER;
+  if (!st && (op <= 2 || op == 5) && !fq_from_be(&y, b + 32 * i)) st = ST_NOT_MEMBER;
+  if (!st) {
+    if (op == 0) r = fq_mul(x, y);
+    else if (op == 1) r = fq_add(x, y);
+    else if (op == 2) r = fq_sub(x, y);
+    else if (op == 3) r = fq_inv(x);
+    else if (op == 4) { if (!fq_sqrt(&r, x)) st = ST_NOT_MEMBER; }
+    else if (op == 5) r = fq_mul_portable(x, y);
+    else st = ST_INVALID_ENCODING;
+  }
+  status[i] = (uint8_t)st;
+  if (st) r = fq_zero();
+  fq_to_be(out + 32 * i, r);
+}
+
+__global__ void __launch_bounds__(BN_BLOCK) k_fq12_op(int op, const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, size_t n,
+                                                      uint8_t* __restrict__ out, uint8_t* __restrict__ status) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  fq12 x, y, r;
+  int st = ST_OK;
+  if (!fq12_from_be(&x, a + 384 * i)) st = ST_NOT_MEMBER;
+  if (!st) {
+    if (op == 0) {
+      if (!fq12_from_be(&y, b + 384 * i)) st = ST_NOT_MEMBER;
+      else fq12_mul(&r, &x, &y);
+    } else if (op == 1) fq12_sqr(&r, &x);
+    else if (op == 2) fq12_inv(&r, &x);
+    else if (op == 3) fq12_cyclotomic_sqr(&r, &x);
+    else if (op >= 4 && op <= 6) fq12_frobenius(&r, &x, op - 3);
+    else if (op == 7) fq12_conj(&r, &x);
+    else st = ST_INVALID_ENCODING;
+  }
+  status[i] = (uint8_t)st;
+  if (st) {
+    for (int k = 0; k < 384; k++) out[384 * i + k] = 0;
+  } else {
+    fq12_to_be(out + 384 * i, &r);
+  }
+}
+
+// generic per-item map kernel for the light-weight entry points (codecs, key derivation, scalar multiplication)
+enum { OP_G1_MUL, OP_G2_MUL, OP_DERIVE_G1, OP_DERIVE_G2, OP_G1_COMPRESS, OP_G1_DECOMPRESS, OP_G2_COMPRESS, OP_G2_DECOMPRESS, OP_G1_VALIDATE, OP_G2_VALIDATE };
+template <int OP>
+__global__ void __launch_bounds__(BN_BLOCK) k_item_op(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, size_t n,
+                                                      uint8_t* __restrict__ out, uint8_t* __restrict__ status) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int st = ST_OK;
+  if (OP == OP_G1_MUL) st = item_g1_mul(out + 64 * i, a + 64 * i, b + 32 * i);
+  else if (OP == OP_G2_MUL) st = item_g2_mul(out + 128 * i, a + 128 * i, b + 32 * i);
+  else if (OP == OP_DERIVE_G1) item_derive_pk_g1(out + 64 * i, a + 32 * i);
+  else if (OP == OP_DERIVE_G2) item_derive_pk_g2(out + 128 * i, a + 32 * i);
+  else if (OP == OP_G1_COMPRESS) {
+    st = item_g1_compress(out + 33 * i, a + 64 * i);
+    if (st) for (int k = 0; k < 33; k++) out[33 * i + k] = 0;
+  } else if (OP == OP_G1_DECOMPRESS) st = item_g1_decompress(out + 64 * i, a + 33 * i);
+  else if (OP == OP_G2_COMPRESS) {
+    st = item_g2_compress(out + 65 * i, a + 128 * i);
+    if (st) for (int k = 0; k < 65; k++) out[65 * i + k] = 0;
+  } else if (OP == OP_G2_DECOMPRESS) st = item_g2_decompress(out + 128 * i, a + 65 * i);
+  else if (OP == OP_G1_VALIDATE) st = item_g1_validate(a + 64 * i);
+  else if (OP == OP_G2_VALIDATE) st = item_g2_validate(a + 128 * i);
+  if (status) status[i] = (uint8_t)st;
+}
+
+// ---- point aggregation: strided mixed additions per thread, then a shared-memory tree per block
+template <class F> struct pt_io;
+template <> struct pt_io<fq> {
+  static const int BYTES = 64;
+  static __device__ int load(jac<fq>* p, const uint8_t* b) { return g1_from_raw(p, b); }
+  static __device__ void store(uint8_t* b, const jac<fq>* p) { g1_to_raw(b, p); }
+};
+template <> struct pt_io<fq2> {
+  static const int BYTES = 128;
+  static __device__ int load(jac<fq2>* p, const uint8_t* b) { return g2_from_raw(p, b); }
+  static __device__ void store(uint8_t* b, const jac<fq2>* p) { g2_to_raw(b, p); }
+};
+__device__ __forceinline__ void record_error(unsigned long long* err, size_t i, int st) {
+  atomicMin(err, ((unsigned long long)i << 8) | (unsigned long long)st);
+}
+
+template <class F>
+__global__ void __launch_bounds__(BN_BLOCK) k_sum_partial(const uint8_t* __restrict__ pts, const uint8_t* __restrict__ neg, size_t n,
+                                                          jac<F>* __restrict__ partial, unsigned long long* __restrict__ err) {
+  __shared__ jac<F> sh[BN_BLOCK];
+  const int B = pt_io<F>::BYTES;
+  jac<F> acc;
+  pt_set_inf(&acc);
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    jac<F> p;
+    int st = pt_io<F>::load(&p, pts + (size_t)B * i);
+    if (st) {
+      record_error(err, i, st);
+      continue;
+    }
+    if (pt_is_inf(&p)) continue;
+    if (neg && neg[i]) p.y = fe_neg(p.y);
+    pt_madd(&acc, &acc, &p.x, &p.y);
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = BN_BLOCK / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) pt_add(&sh[threadIdx.x], &sh[threadIdx.x], &sh[threadIdx.x + s]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+template <class F>
+__global__ void __launch_bounds__(BN_BLOCK) k_sum_final(const jac<F>* __restrict__ partial, int m, uint8_t* __restrict__ out,
+                                                        const unsigned long long* __restrict__ err, uint8_t* __restrict__ status) {
+  __shared__ jac<F> sh[BN_BLOCK];
+  jac<F> acc;
+  pt_set_inf(&acc);
+  for (int i = threadIdx.x; i < m; i += BN_BLOCK) pt_add(&acc, &acc, &partial[i]);
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = BN_BLOCK / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) pt_add(&sh[threadIdx.x], &sh[threadIdx.x], &sh[threadIdx.x + s]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    unsigned long long e = *err;
+    if (e != ~0ull) {
+      *status = (uint8_t)(e & 0xff);
+      for (int k = 0; k < pt_io<F>::BYTES; k++) out[k] = 0;
+    } else {
+      *status = 0;
+      pt_io<F>::store(out, &sh[0]);
+    }
+  }
+}
+
+// ---- distinct-message multi-pairing: every thread folds the Miller values of its strided pairs into one Fq12
+__global__ void __launch_bounds__(BN_PROD_BLOCK) k_distinct_partial(const g1aff* __restrict__ H, const uint8_t* __restrict__ hstatus,
+                                                                     const uint8_t* __restrict__ pks, size_t n, fq12* __restrict__ partial,
+                                                                     unsigned long long* __restrict__ err) {
+  __shared__ fq12 sh[BN_PROD_BLOCK];
+  fq12 acc;
+  fq12_set_one(&acc);
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    if (hstatus[i]) {
+      record_error(err, i, hstatus[i]);
+      continue;
+    }
+    g2j q;
+    int st = g2_from_raw(&q, pks + 128 * i);
+    if (st) {
+      record_error(err, i, st);
+      continue;
+    }
+    if (pt_is_inf(&q)) continue;
+    g1aff h = H[i];
+    fq12 t;
+    miller_loop_2(&t, true, &h.x, &h.y, &q.x, &q.y, false, &h.x, &h.y, (const line_t*)0);
+    fq12_mul(&acc, &acc, &t);
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = BN_PROD_BLOCK / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) fq12_mul(&sh[threadIdx.x], &sh[threadIdx.x], &sh[threadIdx.x + s]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+// product of m Fq12 partials -> one Fq12 (Montgomery form) and its 384-byte big-endian image
+__global__ void __launch_bounds__(BN_PROD_BLOCK) k_fq12_prod_final(const fq12* __restrict__ partial, int m, fq12* __restrict__ out,
+                                                                    uint8_t* __restrict__ out_be, const unsigned long long* __restrict__ err,
+                                                                    uint8_t* __restrict__ status) {
+  __shared__ fq12 sh[BN_PROD_BLOCK];
+  fq12 acc;
+  fq12_set_one(&acc);
+  for (int i = threadIdx.x; i < m; i += BN_PROD_BLOCK) {
+    fq12 t = partial[i];
+    fq12_mul(&acc, &acc, &t);
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = BN_PROD_BLOCK / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) fq12_mul(&sh[threadIdx.x], &sh[threadIdx.x], &sh[threadIdx.x + s]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    if (out) *out = sh[0];
+    if (out_be) fq12_to_be(out_be, &sh[0]);
+    if (status) {
+      unsigned long long e = *err;
+      *status = (e == ~0ull) ? 0 : (uint8_t)(e & 0xff);  // first failing item by index
+    }
+  }
+}
+// prod(partials) * miller(agg_sig, -G2), final exponentiation, verdict
+__global__ void k_distinct_finish(const uint8_t* __restrict__ partials_be, int m, const uint8_t* __restrict__ agg_sig,
+                                  const line_t* __restrict__ lines, uint8_t* __restrict__ status) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  fq12 acc, t;
+  fq12_set_one(&acc);
+  for (int i = 0; i < m; i++) {
+    if (!fq12_from_be(&t, partials_be + 384 * i)) {
+      *status = ST_NOT_MEMBER;
+      return;
+    }
+    fq12_mul(&acc, &acc, &t);
+  }
+  g1j s;
+  int st = g1_from_raw(&s, agg_sig);
+  if (st) {
+    *status = (uint8_t)st;
+    return;
+  }
+  if (!pt_is_inf(&s)) {
+    miller_loop_2(&t, false, &s.x, &s.y, (const fq2*)0, (const fq2*)0, true, &s.x, &s.y, lines);
+    fq12_mul(&acc, &acc, &t);
+  }
+  *status = item_final_exp_is_one(&acc);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+struct bn254_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  line_t* d_lines = nullptr;
+  uint64_t launches = 0;
+  std::string err;
+  // optional per-phase timing of the verify pipeline (bn254_set_profiling): events recorded on `stream`
+  bool prof = false;
+  std::vector<cudaEvent_t> prof_ev;  // groups of 4: before hash, after hash, after miller, after final exp
+};
+static thread_local std::string g_create_err;
+
+#define CK(call)                                                                                          \
+  do {                                                                                                    \
+    cudaError_t e_ = (call);                                                                              \
+    if (e_ != cudaSuccess) {                                                                              \
+      char buf_[512];                                                                                     \
+      snprintf(buf_, sizeof buf_, "%s:%d: %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      ctx->err = buf_;                                                                                    \
+      return BN254_E_CUDA;                                                                                \
+    }                                                                                                     \
+  } while (0)
+
+static inline unsigned grid_for(size_t n, int block = BN_BLOCK) { return (unsigned)((n + block - 1) / block); }
+
+// RAII device buffer on the context's stream (stream-ordered pool allocation)
+struct dbuf {
+  bn254_ctx* ctx;
+  void* p = nullptr;
+  dbuf(bn254_ctx* c) : ctx(c) {}
+  cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 1, ctx->stream); }
+  ~dbuf() {
+    if (p) cudaFreeAsync(p, ctx->stream);
+  }
+  template <class T> T* as() { return (T*)p; }
+};
+
+extern "C" {
+
+int bn254_ctx_create(int device, bn254_ctx** out) {
+  if (!out) return BN254_E_ARG;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    g_create_err = std::string("no CUDA device available (") + cudaGetErrorString(e) + "): this engine has no CPU fallback";
+    return BN254_E_CUDA;
+  }
+  if (device < 0 || device >= count) {
+    g_create_err = "device index out of range";
+    return BN254_E_ARG;
+  }
+  bn254_ctx* ctx = new bn254_ctx();
+  ctx->device = device;
+  auto fail = [&](const char* what, cudaError_t ee) {
+    g_create_err = std::string(what) + ": " + cudaGetErrorString(ee);
+    delete ctx;
+    return BN254_E_CUDA;
+  };
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return fail("cudaSetDevice", e);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail("cudaGetDeviceProperties", e);
+  ctx->sm_count = prop.multiProcessorCount;
+  if ((e = cudaDeviceSetLimit(cudaLimitStackSize, 16 * 1024)) != cudaSuccess) return fail("cudaDeviceSetLimit(stack)", e);
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t thr = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  if ((e = cudaMalloc(&ctx->d_lines, sizeof(line_t) * K_N_LINES)) != cudaSuccess) return fail("cudaMalloc(lines)", e);
+  k_init_lines<<<1, 1, 0, ctx->stream>>>(ctx->d_lines);
+  ctx->launches++;
+  if ((e = cudaGetLastError()) != cudaSuccess) return fail("k_init_lines launch", e);
+  if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return fail("k_init_lines", e);
+  *out = ctx;
+  return 0;
+}
+
+void bn254_ctx_destroy(bn254_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->d_lines) cudaFree(ctx->d_lines);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+const char* bn254_last_error(bn254_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+int bn254_sync(bn254_ctx* ctx) {
+  if (!ctx) return BN254_E_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+void* bn254_stream(bn254_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int bn254_sm_count(bn254_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+uint64_t bn254_launch_count(bn254_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"
+
+#define LAUNCH(kern, grid, block, ...)                        \
+  do {                                                        \
+    kern<<<(grid), (block), 0, ctx->stream>>>(__VA_ARGS__);   \
+    ctx->launches++;                                          \
+    CK(cudaGetLastError());                                   \
+  } while (0)
+#define ARGCHECK(cond)                            \
+  do {                                            \
+    if (!(cond)) {                                \
+      if (ctx) ctx->err = "bad argument: " #cond; \
+      return BN254_E_ARG;                         \
+    }                                             \
+  } while (0)
+#define ENTER()                \
+  ARGCHECK(ctx != nullptr);    \
+  CK(cudaSetDevice(ctx->device))
+#define H2D(dst, src, bytes) CK(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyHostToDevice, ctx->stream))
+#define D2H(dst, src, bytes) CK(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, ctx->stream))
+#define DALLOC(name, bytes) \
+  dbuf name(ctx);           \
+  CK(name.alloc(bytes))
+
+// ---- device-pointer pipelines (asynchronous on ctx->stream)
+static int hash_dev(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, const uint64_t* offsets, size_t n, g1aff* H, uint8_t* status,
+                    uint8_t* tries) {
+  if (n == 0) return 0;
+  LAUNCH(k_hash_to_g1, grid_for(n), BN_BLOCK, msgs, msg_len, offsets, n, H, status, tries);
+  return 0;
+}
+
+extern "C" {
+
+int bn254_hash_to_g1_batch_dev(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, size_t n, uint8_t* g1_out, uint8_t* status) {
+  ENTER();
+  if (n == 0) return 0;
+  DALLOC(H, sizeof(g1aff) * n);
+  int rc = hash_dev(ctx, msgs, msg_len, nullptr, n, H.as<g1aff>(), status, nullptr);
+  if (rc) return rc;
+  LAUNCH(k_g1aff_to_raw, grid_for(n), BN_BLOCK, H.as<g1aff>(), status, n, g1_out);
+  return 0;
+}
+int bn254_hash_to_g1_batch(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, size_t n, uint8_t* g1_out, uint8_t* status) {
+  ENTER();
+  if (n == 0) return 0;
+  ARGCHECK(msgs || msg_len == 0);
+  ARGCHECK(g1_out && status);
+  DALLOC(d_msgs, msg_len * n);
+  DALLOC(d_out, 64 * n);
+  DALLOC(d_st, n);
+  if (msg_len) H2D(d_msgs.p, msgs, msg_len * n);
+  int rc = bn254_hash_to_g1_batch_dev(ctx, d_msgs.as<uint8_t>(), msg_len, n, d_out.as<uint8_t>(), d_st.as<uint8_t>());
+  if (rc) return rc;
+  D2H(g1_out, d_out.p, 64 * n);
+  D2H(status, d_st.p, n);
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int bn254_hash_to_g1_var(bn254_ctx* ctx, const uint8_t* msgs, const uint64_t* offsets, size_t n, uint8_t* g1_out, uint8_t* status,
+                         uint8_t* tries_out) {
+  ENTER();
+  if (n == 0) return 0;
+  ARGCHECK(offsets && g1_out && status);
+  size_t total = offsets[n];
+  DALLOC(d_msgs, total);
+  DALLOC(d_off, 8 * (n + 1));
+  DALLOC(d_out, 64 * n);
+  DALLOC(d_st, n);
+  DALLOC(d_tr, n);
+  DALLOC(H, sizeof(g1aff) * n);
+  if (total) H2D(d_msgs.p, msgs, total);
+  H2D(d_off.p, offsets, 8 * (n + 1));
+  int rc = hash_dev(ctx, d_msgs.as<uint8_t>(), 0, d_off.as<uint64_t>(), n, H.as<g1aff>(), d_st.as<uint8_t>(), d_tr.as<uint8_t>());
+  if (rc) return rc;
+  LAUNCH(k_g1aff_to_raw, grid_for(n), BN_BLOCK, H.as<g1aff>(), d_st.as<uint8_t>(), n, d_out.as<uint8_t>());
+  D2H(g1_out, d_out.p, 64 * n);
+  D2H(status, d_st.p, n);
+  if (tries_out) D2H(tries_out, d_tr.p, n);
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int bn254_sign_batch_dev(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, const uint8_t* sks, size_t n, uint8_t* sigs, uint8_t* status) {
+  ENTER();
+  if (n == 0) return 0;
+  DALLOC(H, sizeof(g1aff) * n);
+  int rc = hash_dev(ctx, msgs, msg_len, nullptr, n, H.as<g1aff>(), status, nullptr);
+  if (rc) return rc;
+  LAUNCH(k_sign, grid_for(n), BN_BLOCK, H.as<g1aff>(), sks, n, sigs, status);
+  return 0;
+}
+int bn254_sign_batch(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, const uint8_t* sks, size_t n, uint8_t* sigs, uint8_t* status) {
+  ENTER();
+  if (n == 0) return 0;
+  ARGCHECK((msgs || msg_len == 0) && sks && sigs && status);
+  DALLOC(d_msgs, msg_len * n);
+  DALLOC(d_sks, 32 * n);
+  DALLOC(d_out, 64 * n);
+  DALLOC(d_st, n);
+  if (msg_len) H2D(d_msgs.p, msgs, msg_len * n);
+  H2D(d_sks.p, sks, 32 * n);
+  int rc = bn254_sign_batch_dev(ctx, d_msgs.as<uint8_t>(), msg_len, d_sks.as<uint8_t>(), n, d_out.as<uint8_t>(), d_st.as<uint8_t>());
+  if (rc) return rc;
+  D2H(sigs, d_out.p, 64 * n);
+  D2H(status, d_st.p, n);
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// msgs == NULL: check_public_keys form (first G1 argument = generator, no hashing)
+static int verify_dev_impl(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, const uint8_t* sigs, const uint8_t* pks, size_t n,
+                           uint8_t* status) {
+  const size_t CHUNK = (size_t)1 << 20;
+  size_t cap = n < CHUNK ? n : CHUNK;
+  DALLOC(H, sizeof(g1aff) * cap);
+  DALLOC(F, sizeof(fq12) * cap);
+  for (size_t off = 0; off < n; off += CHUNK) {
+    size_t m = n - off < CHUNK ? n - off : CHUNK;
+    g1aff* h = nullptr;
+    auto mark = [&]() -> cudaError_t {
+      if (!ctx->prof) return cudaSuccess;
+      cudaEvent_t ev;
+      cudaError_t e = cudaEventCreate(&ev);
+      if (e != cudaSuccess) return e;
+      ctx->prof_ev.push_back(ev);
+      return cudaEventRecord(ev, ctx->stream);
+    };
+    CK(mark());
+    if (msgs) {
+      h = H.as<g1aff>();
+      int rc = hash_dev(ctx, msgs + off * msg_len, msg_len, nullptr, m, h, status + off, nullptr);
+      if (rc) return rc;
+    }
+    CK(mark());
+    LAUNCH(k_verify_miller, grid_for(m), BN_BLOCK, h, sigs + 64 * off, pks + 128 * off, m, F.as<fq12>(), status + off, ctx->d_lines);
+    CK(mark());
+    LAUNCH(k_final_exp_check, grid_for(m), BN_BLOCK, F.as<fq12>(), m, status + off);
+    CK(mark());
+  }
+  return 0;
+}
+int bn254_set_profiling(bn254_ctx* ctx, int on) {
+  ENTER();
+  ctx->prof = on != 0;
+  return 0;
+}
+// accumulated device time (ms) of the hash / Miller / final-exponentiation kernels of the verify calls made since the
+// last query; synchronises the stream
+int bn254_phase_ms(bn254_ctx* ctx, float* out3) {
+  ENTER();
+  ARGCHECK(out3 != nullptr);
+  CK(cudaStreamSynchronize(ctx->stream));
+  out3[0] = out3[1] = out3[2] = 0.f;
+  for (size_t g = 0; g + 3 < ctx->prof_ev.size(); g += 4)
+    for (int k = 0; k < 3; k++) {
+      float ms = 0.f;
+      CK(cudaEventElapsedTime(&ms, ctx->prof_ev[g + k], ctx->prof_ev[g + k + 1]));
+      out3[k] += ms;
+    }
+  for (cudaEvent_t ev : ctx->prof_ev) cudaEventDestroy(ev);
+  ctx->prof_ev.clear();
+  return 0;
+}
+int bn254_verify_batch_dev(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, const uint8_t* sigs, const uint8_t* pks, size_t n,
+                           uint8_t* status) {
+  ENTER();
+  if (n == 0) return 0;
+  ARGCHECK(msgs != nullptr);
+  return verify_dev_impl(ctx, msgs, msg_len, sigs, pks, n, status);
+}
+int bn254_verify_batch(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, const uint8_t* sigs, const uint8_t* pks, size_t n,
+                       uint8_t* status) {
+  ENTER();
+  if (n == 0) return 0;
+  ARGCHECK((msgs || msg_len == 0) && sigs && pks && status);
+  DALLOC(d_msgs, msg_len * n + 1);
+  DALLOC(d_sigs, 64 * n);
+  DALLOC(d_pks, 128 * n);
+  DALLOC(d_st, n);
+  if (msg_len) H2D(d_msgs.p, msgs, msg_len * n);
+  H2D(d_sigs.p, sigs, 64 * n);
+  H2D(d_pks.p, pks, 128 * n);
+  int rc = verify_dev_impl(ctx, d_msgs.as<uint8_t>(), msg_len, d_sigs.as<uint8_t>(), d_pks.as<uint8_t>(), n, d_st.as<uint8_t>());
+  if (rc) return rc;
+  D2H(status, d_st.p, n);
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int bn254_check_public_keys_batch(bn254_ctx* ctx, const uint8_t* pk_g2, const uint8_t* pk_g1, size_t n, uint8_t* status) {
+  ENTER();
+  if (n == 0) return 0;
+  ARGCHECK(pk_g2 && pk_g1 && status);
+  DALLOC(d_g1, 64 * n);
+  DALLOC(d_g2, 128 * n);
+  DALLOC(d_st, n);
+  H2D(d_g1.p, pk_g1, 64 * n);
+  H2D(d_g2.p, pk_g2, 128 * n);
+  CK(cudaMemsetAsync(d_st.p, 0, n, ctx->stream));
+  int rc = verify_dev_impl(ctx, nullptr, 0, d_g1.as<uint8_t>(), d_g2.as<uint8_t>(), n, d_st.as<uint8_t>());
+  if (rc) return rc;
+  D2H(status, d_st.p, n);
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int bn254_pairing_check_batch(bn254_ctx* ctx, const uint8_t* g1s, const uint8_t* g2s, size_t k, size_t n, uint8_t* status) {
+  ENTER();
+  if (n == 0) return 0;
+  ARGCHECK(status && (k == 0 || (g1s && g2s)));
+  DALLOC(d_g1, 64 * k * n);
+  DALLOC(d_g2, 128 * k * n);
+  DALLOC(d_st, n);
+  DALLOC(F, sizeof(fq12) * n);
+  if (k) {
+    H2D(d_g1.p, g1s, 64 * k * n);
+    H2D(d_g2.p, g2s, 128 * k * n);
+  }
+  LAUNCH(k_miller_pairs, grid_for(n), BN_BLOCK, d_g1.as<uint8_t>(), d_g2.as<uint8_t>(), k, n, F.as<fq12>(), d_st.as<uint8_t>());
+  LAUNCH(k_final_exp_check, grid_for(n), BN_BLOCK, F.as<fq12>(), n, d_st.as<uint8_t>());
+  D2H(status, d_st.p, n);
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int bn254_miller_loop_batch(bn254_ctx* ctx, const uint8_t* g1s, const uint8_t* g2s, size_t k, size_t n, uint8_t* f_out384, uint8_t* status) {
+  ENTER();
+  if (n == 0) return 0;
+  ARGCHECK(status && f_out384 && (k == 0 || (g1s && g2s)));
+  DALLOC(d_g1, 64 * k * n);
+  DALLOC(d_g2, 128 * k * n);
+  DALLOC(d_st, n);
+  DALLOC(F, sizeof(fq12) * n);
+  DALLOC(d_out, 384 * n);
+  if (k) {
+    H2D(d_g1.p, g1s, 64 * k * n);
+    H2D(d_g2.p, g2s, 128 * k * n);
+  }
+  LAUNCH(k_miller_pairs, grid_for(n), BN_BLOCK, d_g1.as<uint8_t>(), d_g2.as<uint8_t>(), k, n, F.as<fq12>(), d_st.as<uint8_t>());
+  LAUNCH(k_fq12_to_be, grid_for(n), BN_BLOCK, F.as<fq12>(), d_st.as<uint8_t>(), n, d_out.as<uint8_t>());
+  D2H(f_out384, d_out.p, 384 * n);
+  D2H(status, d_st.p, n);
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int bn254_final_exp_batch(bn254_ctx* ctx, const uint8_t* f_in384, size_t n, uint8_t* gt_out384, uint8_t* status) {
+  ENTER();
+  if (n == 0) return 0;
+  ARGCHECK(f_in384 && gt_out384 && status);
+  DALLOC(d_in, 384 * n);
+  DALLOC(d_out, 384 * n);
+  DALLOC(d_st, n);
+  H2D(d_in.p, f_in384, 384 * n);
+  LAUNCH(k_final_exp_bytes, grid_for(n), BN_BLOCK, d_in.as<uint8_t>(), n, d_out.as<uint8_t>(), d_st.as<uint8_t>());
+  D2H(gt_out384, d_out.p, 384 * n);
+  D2H(status, d_st.p, n);
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int bn254_fq_op_batch(bn254_ctx* ctx, int op, const uint8_t* a32, const uint8_t* b32, size_t n, uint8_t* out32, uint8_t* status) {
+  ENTER();
+  if (n == 0) return 0;
+  ARGCHECK(a32 && out32 && status);
+  DALLOC(d_a, 32 * n);
+  DALLOC(d_b, 32 * n);
+  DALLOC(d_out, 32 * n);
+  DALLOC(d_st, n);
+  H2D(d_a.p, a32, 32 * n);
+  if (b32) H2D(d_b.p, b32, 32 * n);
+  else CK(cudaMemsetAsync(d_b.p, 0, 32 * n, ctx->stream));
+  LAUNCH(k_fq_op, grid_for(n), BN_BLOCK, op, d_a.as<uint8_t>(), d_b.as<uint8_t>(), n, d_out.as<uint8_t>(), d_st.as<uint8_t>());
+  D2H(out32, d_out.p, 32 * n);
+  D2H(status, d_st.p, n);
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int bn254_fq12_op_batch(bn254_ctx* ctx, int op, const uint8_t* a384, const uint8_t* b384, size_t n, uint8_t* out384, uint8_t* status) {
+  ENTER();
+  if (n == 0) return 0;
+  ARGCHECK(a384 && out384 && status);
+  DALLOC(d_a, 384 * n);
+  DALLOC(d_b, 384 * n);
+  DALLOC(d_out, 384 * n);
+  DALLOC(d_st, n);
+  H2D(d_a.p, a384, 384 * n);
+  if (b384) H2D(d_b.p, b384, 384 * n);
+  else CK(cudaMemsetAsync(d_b.p, 0, 384 * n, ctx->stream));
+  LAUNCH(k_fq12_op, grid_for(n), BN_BLOCK, op, d_a.as<uint8_t>(), d_b.as<uint8_t>(), n, d_out.as<uint8_t>(), d_st.as<uint8_t>());
+  D2H(out384, d_out.p, 384 * n);
+  D2H(status, d_st.p, n);
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+}  // extern "C"
+
+// generic host wrapper of k_item_op
+template <int OP>
+static int item_op_host(bn254_ctx* ctx, const uint8_t* a, size_t a_bytes, const uint8_t* b, size_t b_bytes, size_t n, uint8_t* out,
+                        size_t out_bytes, uint8_t* status) {
+  ENTER();
+  if (n == 0) return 0;
+  ARGCHECK(a != nullptr && (b_bytes == 0 || b != nullptr));
+  DALLOC(d_a, a_bytes * n);
+  DALLOC(d_b, b_bytes * n);
+  DALLOC(d_out, out_bytes * n);
+  DALLOC(d_st, n);
+  H2D(d_a.p, a, a_bytes * n);
+  if (b_bytes) H2D(d_b.p, b, b_bytes * n);
+  LAUNCH(k_item_op<OP>, grid_for(n), BN_BLOCK, d_a.as<uint8_t>(), d_b.as<uint8_t>(), n, d_out.as<uint8_t>(), d_st.as<uint8_t>());
+  if (out && out_bytes) D2H(out, d_out.p, out_bytes * n);
+  if (status) D2H(status, d_st.p, n);
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+template <class F>
+static int sum_dev_impl(bn254_ctx* ctx, const uint8_t* pts, const uint8_t* neg, size_t n, uint8_t* out, uint8_t* status) {
+  size_t want = (n + 7) / 8;  // >= 8 points per thread before the tree
+  size_t max_blocks = (size_t)ctx->sm_count * 4;
+  size_t blocks = (want + BN_BLOCK - 1) / BN_BLOCK;
+  if (blocks > max_blocks) blocks = max_blocks;
+  if (blocks == 0) blocks = 1;
+  DALLOC(partial, sizeof(jac<F>) * blocks);
+  DALLOC(err, 8);
+  CK(cudaMemsetAsync(err.p, 0xff, 8, ctx->stream));
+  LAUNCH(k_sum_partial<F>, (unsigned)blocks, BN_BLOCK, pts, neg, n, partial.as<jac<F>>(), err.as<unsigned long long>());
+  LAUNCH(k_sum_final<F>, 1, BN_BLOCK, partial.as<jac<F>>(), (int)blocks, out, err.as<unsigned long long>(), status);
+  return 0;
+}
+template <class F>
+static int sum_host_impl(bn254_ctx* ctx, const uint8_t* pts, const uint8_t* neg, size_t n, uint8_t* out, uint8_t* status) {
+  const size_t B = pt_io<F>::BYTES;
+  ARGCHECK(out && status && (n == 0 || pts));
+  DALLOC(d_pts, B * n);
+  DALLOC(d_neg, n);
+  DALLOC(d_out, B);
+  DALLOC(d_st, 1);
+  if (n) H2D(d_pts.p, pts, B * n);
+  if (n && neg) H2D(d_neg.p, neg, n);
+  int rc = sum_dev_impl<F>(ctx, d_pts.as<uint8_t>(), neg ? d_neg.as<uint8_t>() : nullptr, n, d_out.as<uint8_t>(), d_st.as<uint8_t>());
+  if (rc) return rc;
+  D2H(out, d_out.p, B);
+  D2H(status, d_st.p, 1);
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// Miller-product partial of (H(msg_i), pk_i), i < n  ->  f_be (384 bytes, device) ; status = first error or 0
+static int distinct_partial_dev(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, const uint8_t* pks, size_t n, uint8_t* f_be,
+                                uint8_t* status) {
+  size_t cap = n ? n : 1;
+  DALLOC(H, sizeof(g1aff) * cap);
+  DALLOC(hst, cap);
+  DALLOC(err, 8);
+  CK(cudaMemsetAsync(err.p, 0xff, 8, ctx->stream));
+  int rc = hash_dev(ctx, msgs, msg_len, nullptr, n, H.as<g1aff>(), hst.as<uint8_t>(), nullptr);
+  if (rc) return rc;
+  size_t max_blocks = (size_t)ctx->sm_count * 4;
+  size_t blocks = (n + BN_PROD_BLOCK - 1) / BN_PROD_BLOCK;
+  if (blocks > max_blocks) blocks = max_blocks;
+  if (blocks == 0) blocks = 1;
+  DALLOC(partial, sizeof(fq12) * blocks);
+  LAUNCH(k_distinct_partial, (unsigned)blocks, BN_PROD_BLOCK, H.as<g1aff>(), hst.as<uint8_t>(), pks, n, partial.as<fq12>(),
+         err.as<unsigned long long>());
+  LAUNCH(k_fq12_prod_final, 1, BN_PROD_BLOCK, partial.as<fq12>(), (int)blocks, (fq12*)nullptr, f_be, err.as<unsigned long long>(), status);
+  return 0;
+}
+
+extern "C" {
+
+int bn254_g1_mul_batch(bn254_ctx* ctx, const uint8_t* pts, const uint8_t* scalars, size_t n, uint8_t* out64, uint8_t* status) {
+  return item_op_host<OP_G1_MUL>(ctx, pts, 64, scalars, 32, n, out64, 64, status);
+}
+int bn254_g2_mul_batch(bn254_ctx* ctx, const uint8_t* pts, const uint8_t* scalars, size_t n, uint8_t* out128, uint8_t* status) {
+  return item_op_host<OP_G2_MUL>(ctx, pts, 128, scalars, 32, n, out128, 128, status);
+}
+int bn254_derive_pk_g1_batch(bn254_ctx* ctx, const uint8_t* sks, size_t n, uint8_t* out64) {
+  return item_op_host<OP_DERIVE_G1>(ctx, sks, 32, nullptr, 0, n, out64, 64, nullptr);
+}
+int bn254_derive_pk_g2_batch(bn254_ctx* ctx, const uint8_t* sks, size_t n, uint8_t* out128) {
+  return item_op_host<OP_DERIVE_G2>(ctx, sks, 32, nullptr, 0, n, out128, 128, nullptr);
+}
+int bn254_g1_compress_batch(bn254_ctx* ctx, const uint8_t* raw64, size_t n, uint8_t* out33, uint8_t* status) {
+  return item_op_host<OP_G1_COMPRESS>(ctx, raw64, 64, nullptr, 0, n, out33, 33, status);
+}
+int bn254_g1_decompress_batch(bn254_ctx* ctx, const uint8_t* in33, size_t n, uint8_t* out64, uint8_t* status) {
+  return item_op_host<OP_G1_DECOMPRESS>(ctx, in33, 33, nullptr, 0, n, out64, 64, status);
+}
+int bn254_g2_compress_batch(bn254_ctx* ctx, const uint8_t* raw128, size_t n, uint8_t* out65, uint8_t* status) {
+  return item_op_host<OP_G2_COMPRESS>(ctx, raw128, 128, nullptr, 0, n, out65, 65, status);
+}
+int bn254_g2_decompress_batch(bn254_ctx* ctx, const uint8_t* in65, size_t n, uint8_t* out128, uint8_t* status) {
+  return item_op_host<OP_G2_DECOMPRESS>(ctx, in65, 65, nullptr, 0, n, out128, 128, status);
+}
+int bn254_g1_validate_batch(bn254_ctx* ctx, const uint8_t* raw64, size_t n, uint8_t* status) {
+  return item_op_host<OP_G1_VALIDATE>(ctx, raw64, 64, nullptr, 0, n, nullptr, 0, status);
+}
+int bn254_g2_validate_batch(bn254_ctx* ctx, const uint8_t* raw128, size_t n, uint8_t* status) {
+  return item_op_host<OP_G2_VALIDATE>(ctx, raw128, 128, nullptr, 0, n, nullptr, 0, status);
+}
+
+int bn254_g1_sum_dev(bn254_ctx* ctx, const uint8_t* pts, const uint8_t* neg, size_t n, uint8_t* out64, uint8_t* status) {
+  ENTER();
+  return sum_dev_impl<fq>(ctx, pts, neg, n, out64, status);
+}
+int bn254_g2_sum_dev(bn254_ctx* ctx, const uint8_t* pts, const uint8_t* neg, size_t n, uint8_t* out128, uint8_t* status) {
+  ENTER();
+  return sum_dev_impl<fq2>(ctx, pts, neg, n, out128, status);
+}
+int bn254_g1_sum(bn254_ctx* ctx, const uint8_t* pts, const uint8_t* neg, size_t n, uint8_t* out64, uint8_t* status) {
+  ENTER();
+  return sum_host_impl<fq>(ctx, pts, neg, n, out64, status);
+}
+int bn254_g2_sum(bn254_ctx* ctx, const uint8_t* pts, const uint8_t* neg, size_t n, uint8_t* out128, uint8_t* status) {
+  ENTER();
+  return sum_host_impl<fq2>(ctx, pts, neg, n, out128, status);
+}
+
+int bn254_aggregate_verify_same_msg(bn254_ctx* ctx, const uint8_t* msg, size_t msg_len, const uint8_t* sigs, const uint8_t* pks, size_t n,
+                                    uint8_t* status) {
+  ENTER();
+  ARGCHECK(status && (msg || msg_len == 0) && (n == 0 || (sigs && pks)));
+  DALLOC(d_msg, msg_len + 1);
+  DALLOC(d_sigs, 64 * n);
+  DALLOC(d_pks, 128 * n);
+  DALLOC(d_asig, 64);
+  DALLOC(d_apk, 128);
+  DALLOC(d_st, 4);
+  if (msg_len) H2D(d_msg.p, msg, msg_len);
+  if (n) {
+    H2D(d_sigs.p, sigs, 64 * n);
+    H2D(d_pks.p, pks, 128 * n);
+  }
+  uint8_t* st = d_st.as<uint8_t>();
+  int rc = sum_dev_impl<fq>(ctx, d_sigs.as<uint8_t>(), nullptr, n, d_asig.as<uint8_t>(), st + 0);
+  if (rc) return rc;
+  rc = sum_dev_impl<fq2>(ctx, d_pks.as<uint8_t>(), nullptr, n, d_apk.as<uint8_t>(), st + 1);
+  if (rc) return rc;
+  rc = verify_dev_impl(ctx, d_msg.as<uint8_t>(), msg_len, d_asig.as<uint8_t>(), d_apk.as<uint8_t>(), 1, st + 2);
+  if (rc) return rc;
+  uint8_t h[4] = {0, 0, 0, 0};
+  D2H(h, d_st.p, 3);
+  CK(cudaStreamSynchronize(ctx->stream));
+  *status = h[0] ? h[0] : (h[1] ? h[1] : h[2]);
+  return 0;
+}
+
+int bn254_miller_partial_distinct_dev(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, const uint8_t* pks, size_t n, uint8_t* f_out384,
+                                      uint8_t* status) {
+  ENTER();
+  return distinct_partial_dev(ctx, msgs, msg_len, pks, n, f_out384, status);
+}
+int bn254_miller_partial_distinct(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, const uint8_t* pks, size_t n, uint8_t* f_out384,
+                                  uint8_t* status) {
+  ENTER();
+  ARGCHECK(f_out384 && status && (n == 0 || pks));
+  DALLOC(d_msgs, msg_len * n + 1);
+  DALLOC(d_pks, 128 * n);
+  DALLOC(d_f, 384);
+  DALLOC(d_st, 1);
+  if (n && msg_len) H2D(d_msgs.p, msgs, msg_len * n);
+  if (n) H2D(d_pks.p, pks, 128 * n);
+  int rc = distinct_partial_dev(ctx, d_msgs.as<uint8_t>(), msg_len, d_pks.as<uint8_t>(), n, d_f.as<uint8_t>(), d_st.as<uint8_t>());
+  if (rc) return rc;
+  D2H(f_out384, d_f.p, 384);
+  D2H(status, d_st.p, 1);
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int bn254_finish_distinct(bn254_ctx* ctx, const uint8_t* partials384, size_t n_partials, const uint8_t* agg_sig, uint8_t* status) {
+  ENTER();
+  ARGCHECK(status && agg_sig && (n_partials == 0 || partials384));
+  DALLOC(d_p, 384 * n_partials);
+  DALLOC(d_sig, 64);
+  DALLOC(d_st, 1);
+  if (n_partials) H2D(d_p.p, partials384, 384 * n_partials);
+  H2D(d_sig.p, agg_sig, 64);
+  LAUNCH(k_distinct_finish, 1, 32, d_p.as<uint8_t>(), (int)n_partials, d_sig.as<uint8_t>(), ctx->d_lines, d_st.as<uint8_t>());
+  D2H(status, d_st.p, 1);
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int bn254_aggregate_verify_distinct(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, const uint8_t* pks, size_t n, const uint8_t* agg_sig,
+                                    uint8_t* status) {
+  uint8_t f[384], st = 0;
+  int rc = bn254_miller_partial_distinct(ctx, msgs, msg_len, pks, n, f, &st);
+  if (rc) return rc;
+  if (st) {
+    *status = st;
+    return 0;
+  }
+  return bn254_finish_distinct(ctx, f, 1, agg_sig, status);
+}
+
+}  // extern "C"

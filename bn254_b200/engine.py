@@ -1,0 +1,224 @@
+"""Batch entry points over host byte buffers (thin, typed wrappers of the C ABI).
+
+Buffers are `bytes` (or anything exposing the buffer protocol through numpy / torch); results are `bytes`.
+Statuses are one byte per item: 0 = Ok, otherwise the Error variant of /root/reference/src/error.rs:6-29.
+"""
+from ._native import Context, S, I, out
+
+_default = {}
+
+
+def context(device=0):
+    """Process-wide context per device (created on first use; raises EngineError without a GPU)."""
+    c = _default.get(device)
+    if c is None:
+        c = _default[device] = Context(device)
+    return c
+
+
+def _n(buf, size):
+    assert len(buf) % size == 0, "buffer length %d is not a multiple of %d" % (len(buf), size)
+    return len(buf) // size
+
+
+def hash_to_g1_batch(msgs, msg_len, n, ctx=None):
+    ctx = ctx or context()
+    o, st = out(64 * n), out(n)
+    ctx.call("bn254_hash_to_g1_batch", msgs, S(msg_len), S(n), o, st)
+    return o.raw[:64 * n], st.raw[:n]
+
+
+def hash_to_g1_var(msgs_list, ctx=None):
+    import struct
+    ctx = ctx or context()
+    n = len(msgs_list)
+    offs = [0]
+    for m in msgs_list:
+        offs.append(offs[-1] + len(m))
+    blob = b"".join(msgs_list)
+    o, st, tr = out(64 * n), out(n), out(n)
+    ctx.call("bn254_hash_to_g1_var", blob if blob else None, struct.pack("<%dQ" % (n + 1), *offs), S(n), o, st, tr)
+    return o.raw[:64 * n], st.raw[:n], tr.raw[:n]
+
+
+def sign_batch(msgs, msg_len, sks, ctx=None):
+    ctx = ctx or context()
+    n = _n(sks, 32)
+    o, st = out(64 * n), out(n)
+    ctx.call("bn254_sign_batch", msgs, S(msg_len), sks, S(n), o, st)
+    return o.raw[:64 * n], st.raw[:n]
+
+
+def verify_batch(msgs, msg_len, sigs, pks, ctx=None):
+    ctx = ctx or context()
+    n = _n(sigs, 64)
+    assert _n(pks, 128) == n
+    st = out(n)
+    ctx.call("bn254_verify_batch", msgs, S(msg_len), sigs, pks, S(n), st)
+    return st.raw[:n]
+
+
+def check_public_keys_batch(pk_g2, pk_g1, ctx=None):
+    ctx = ctx or context()
+    n = _n(pk_g1, 64)
+    st = out(n)
+    ctx.call("bn254_check_public_keys_batch", pk_g2, pk_g1, S(n), st)
+    return st.raw[:n]
+
+
+def pairing_check_batch(g1s, g2s, k, n, ctx=None):
+    ctx = ctx or context()
+    st = out(n)
+    ctx.call("bn254_pairing_check_batch", g1s if k else None, g2s if k else None, S(k), S(n), st)
+    return st.raw[:n]
+
+
+def miller_loop_batch(g1s, g2s, k, n, ctx=None):
+    ctx = ctx or context()
+    o, st = out(384 * n), out(n)
+    ctx.call("bn254_miller_loop_batch", g1s if k else None, g2s if k else None, S(k), S(n), o, st)
+    return o.raw[:384 * n], st.raw[:n]
+
+
+def final_exp_batch(f, ctx=None):
+    ctx = ctx or context()
+    n = _n(f, 384)
+    o, st = out(384 * n), out(n)
+    ctx.call("bn254_final_exp_batch", f, S(n), o, st)
+    return o.raw[:384 * n], st.raw[:n]
+
+
+def fq_op_batch(op, a, b=None, ctx=None):
+    ctx = ctx or context()
+    n = _n(a, 32)
+    o, st = out(32 * n), out(n)
+    ctx.call("bn254_fq_op_batch", I(op), a, b, S(n), o, st)
+    return o.raw[:32 * n], st.raw[:n]
+
+
+def fq12_op_batch(op, a, b=None, ctx=None):
+    ctx = ctx or context()
+    n = _n(a, 384)
+    o, st = out(384 * n), out(n)
+    ctx.call("bn254_fq12_op_batch", I(op), a, b, S(n), o, st)
+    return o.raw[:384 * n], st.raw[:n]
+
+
+def g1_sum(pts, neg=None, ctx=None):
+    ctx = ctx or context()
+    n = _n(pts, 64)
+    o, st = out(64), out(1)
+    ctx.call("bn254_g1_sum", pts if n else None, neg, S(n), o, st)
+    return o.raw[:64], st.raw[0]
+
+
+def g2_sum(pts, neg=None, ctx=None):
+    ctx = ctx or context()
+    n = _n(pts, 128)
+    o, st = out(128), out(1)
+    ctx.call("bn254_g2_sum", pts if n else None, neg, S(n), o, st)
+    return o.raw[:128], st.raw[0]
+
+
+def derive_pk_g2_batch(sks, ctx=None):
+    ctx = ctx or context()
+    n = _n(sks, 32)
+    o = out(128 * n)
+    ctx.call("bn254_derive_pk_g2_batch", sks, S(n), o)
+    return o.raw[:128 * n]
+
+
+def derive_pk_g1_batch(sks, ctx=None):
+    ctx = ctx or context()
+    n = _n(sks, 32)
+    o = out(64 * n)
+    ctx.call("bn254_derive_pk_g1_batch", sks, S(n), o)
+    return o.raw[:64 * n]
+
+
+def g1_mul_batch(pts, scalars, ctx=None):
+    ctx = ctx or context()
+    n = _n(pts, 64)
+    o, st = out(64 * n), out(n)
+    ctx.call("bn254_g1_mul_batch", pts, scalars, S(n), o, st)
+    return o.raw[:64 * n], st.raw[:n]
+
+
+def g2_mul_batch(pts, scalars, ctx=None):
+    ctx = ctx or context()
+    n = _n(pts, 128)
+    o, st = out(128 * n), out(n)
+    ctx.call("bn254_g2_mul_batch", pts, scalars, S(n), o, st)
+    return o.raw[:128 * n], st.raw[:n]
+
+
+def _codec(name, data, in_size, out_size, ctx):
+    ctx = ctx or context()
+    n = _n(data, in_size)
+    o, st = out(out_size * n), out(n)
+    ctx.call(name, data, S(n), o, st)
+    return o.raw[:out_size * n], st.raw[:n]
+
+
+def g1_compress_batch(raw, ctx=None):
+    return _codec("bn254_g1_compress_batch", raw, 64, 33, ctx)
+
+
+def g1_decompress_batch(comp, ctx=None):
+    return _codec("bn254_g1_decompress_batch", comp, 33, 64, ctx)
+
+
+def g2_compress_batch(raw, ctx=None):
+    return _codec("bn254_g2_compress_batch", raw, 128, 65, ctx)
+
+
+def g2_decompress_batch(comp, ctx=None):
+    return _codec("bn254_g2_decompress_batch", comp, 65, 128, ctx)
+
+
+def g1_validate_batch(raw, ctx=None):
+    ctx = ctx or context()
+    n = _n(raw, 64)
+    st = out(n)
+    ctx.call("bn254_g1_validate_batch", raw, S(n), st)
+    return st.raw[:n]
+
+
+def g2_validate_batch(raw, ctx=None):
+    ctx = ctx or context()
+    n = _n(raw, 128)
+    st = out(n)
+    ctx.call("bn254_g2_validate_batch", raw, S(n), st)
+    return st.raw[:n]
+
+
+def aggregate_verify_same_msg(msg, sigs, pks, ctx=None):
+    ctx = ctx or context()
+    n = _n(sigs, 64)
+    st = out(1)
+    ctx.call("bn254_aggregate_verify_same_msg", msg if len(msg) else None, S(len(msg)), sigs if n else None, pks if n else None, S(n), st)
+    return st.raw[0]
+
+
+def aggregate_verify_distinct(msgs, msg_len, pks, agg_sig, ctx=None):
+    ctx = ctx or context()
+    n = _n(pks, 128)
+    st = out(1)
+    ctx.call("bn254_aggregate_verify_distinct", msgs if len(msgs) else None, S(msg_len), pks if n else None, S(n), agg_sig, st)
+    return st.raw[0]
+
+
+def miller_partial_distinct(msgs, msg_len, pks, ctx=None):
+    ctx = ctx or context()
+    n = _n(pks, 128)
+    o, st = out(384), out(1)
+    ctx.call("bn254_miller_partial_distinct", msgs if len(msgs) else None, S(msg_len), pks if n else None, S(n), o, st)
+    return o.raw[:384], st.raw[0]
+
+
+def finish_distinct(partials, agg_sig, ctx=None):
+    ctx = ctx or context()
+    n = _n(partials, 384)
+    st = out(1)
+    ctx.call("bn254_finish_distinct", partials if n else None, S(n), agg_sig, st)
+    return st.raw[0]

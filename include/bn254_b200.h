@@ -61,6 +61,11 @@ void* bn254_stream(bn254_ctx* ctx);            /* the cudaStream_t used by every
 int bn254_sm_count(bn254_ctx* ctx);
 uint64_t bn254_launch_count(bn254_ctx* ctx);   /* kernels launched by this context so far */
 
+/* measurement support: when on, the verify pipeline brackets its three kernels (hash, Miller loop, final
+ * exponentiation) with CUDA events on the context's stream; bn254_phase_ms returns and clears the accumulated times */
+int bn254_set_profiling(bn254_ctx* ctx, int on);
+int bn254_phase_ms(bn254_ctx* ctx, float* out3);
+
 /* hash_to_try_and_increment (/root/reference/src/hash.rs:29-63): n messages of msg_len bytes each -> G1 */
 int bn254_hash_to_g1_batch(bn254_ctx*, const uint8_t* msgs, size_t msg_len, size_t n, uint8_t* g1_out, uint8_t* status);
 int bn254_hash_to_g1_batch_dev(bn254_ctx*, const uint8_t* msgs, size_t msg_len, size_t n, uint8_t* g1_out, uint8_t* status);

@@ -1,0 +1,62 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol the header declares,
+and the host-side mirror of the reference API behaves like the crate where no arithmetic is involved."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _lib_ready():
+    from bn254_b200 import build
+    if not os.path.exists(build.OUT):
+        build.build()
+    return build.OUT
+
+
+def test_header_symbols_exported():
+    import ctypes
+    from bn254_b200 import _native
+    hdr = open(os.path.join(ROOT, "include", "bn254_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(bn254_[a-z0-9_]+)\s*\(", hdr)))
+    assert declared, "no declarations parsed"
+    lib = ctypes.CDLL(_lib_ready())
+    for name in declared:
+        assert hasattr(lib, name), "libbn254_b200.so does not export %s" % name
+    assert sorted(_native.SYMBOLS) == declared
+
+
+def test_no_cpu_fallback_and_no_oracle_import():
+    """The product package must not reference oracle/ and must fail loudly when no CUDA device exists."""
+    pkg = os.path.join(ROOT, "bn254_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "pyoracle" not in txt and "bn254_oracle" not in txt and "libhostsim" not in txt, f
+    import torch
+    if not torch.cuda.is_available():
+        import bn254_b200
+        _lib_ready()
+        with pytest.raises(bn254_b200.EngineError):
+            bn254_b200.Context(0)
+
+
+def test_private_key_host_logic():  # /root/reference/src/types_test.rs:14-46
+    from bn254_b200 import Error, PrivateKey
+    h = "2009da7287c158b126123c113d1c85241b6e3294dd75c643588630a8bc0f934c"
+    sk = PrivateKey(bytes.fromhex(h))
+    assert sk.to_bytes().hex() == h and PrivateKey(h).to_hex() == h
+    assert PrivateKey.deserialize(sk.serialize()).to_bytes() == sk.to_bytes() and len(sk.serialize()) == 32
+    for bad in (b"\xaa" * 50, b"\xaa\xaa"):
+        with pytest.raises(Error) as e:
+            PrivateKey(bad)
+        assert e.value.variant == "InvalidLength"
+    with pytest.raises(Error) as e:
+        PrivateKey("zz")
+    assert e.value.variant == "HexDecodeFailed"
+    # keys above r are accepted and reduced (examples/bn254.rs:8,12)
+    big = "c9afa9d845ba75166b5c215767b1d6934e50c3db36e89b127b8a622b120f6721"
+    r = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+    assert int.from_bytes(PrivateKey(big).to_bytes(), "big") == int(big, 16) % r

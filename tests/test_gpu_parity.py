@@ -1,0 +1,405 @@
+"""GPU parity tests: the CUDA engine, called through the C ABI, against the CPU oracle on the same seeded inputs,
+against the reference's golden vectors, and -- at full BASELINE sizes -- through size-independent properties.
+Bit-exact everywhere (integer arithmetic).  Run on a B200: `python -m pytest tests -m gpu`."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import synth
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_vectors.json")))
+H = bytes.fromhex
+Q = 0x30644E72E131A029B85045B68181585D97816A916871CA8D3C208C16D87CFD47
+R = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+G1_GEN = (1).to_bytes(32, "big") + (2).to_bytes(32, "big")
+NTHREADS = os.cpu_count() or 1
+
+
+def be(x, n=32):
+    return x.to_bytes(n, "big")
+
+
+@pytest.fixture(scope="module")
+def E():
+    import bn254_b200
+    from bn254_b200 import build, engine
+    build.build()
+    engine.context(0)  # raises without a GPU / the CUDA library: no fallback
+    return engine
+
+
+# ---------------------------------------------------------------------------------------------- field layers
+def test_fq_ptx_product_matches_portable_and_oracle(E):
+    n = 1 << 18
+    rng = np.random.default_rng(5)
+    a = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    b = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    a[:, 0] &= 0x1F  # < 2^253 < q
+    b[:, 0] &= 0x1F
+    edge = [0, 1, 2, Q - 1, Q - 2, (1 << 253) - 1, (Q - 1) // 2]
+    for i, x in enumerate(edge):
+        for j, y in enumerate(edge):
+            a[i * len(edge) + j] = np.frombuffer(be(x), dtype=np.uint8)
+            b[i * len(edge) + j] = np.frombuffer(be(y), dtype=np.uint8)
+    ab, bb = a.tobytes(), b.tobytes()
+    ptx, st = E.fq_op_batch(0, ab, bb)
+    port, st2 = E.fq_op_batch(5, ab, bb)
+    assert not any(st) and not any(st2)
+    assert ptx == port  # PTX even/odd IMAD.WIDE chains == portable CIOS, 2^18 pairs
+    for i in list(range(len(edge) ** 2)) + list(range(1000, 1000 + 4096)):
+        x, y = ab[32 * i:32 * i + 32], bb[32 * i:32 * i + 32]
+        assert ptx[32 * i:32 * i + 32] == O.fq_op(0, x, y)[1]
+    for op in (1, 2):
+        r, st = E.fq_op_batch(op, ab[:32 * 8192], bb[:32 * 8192])
+        for i in range(0, 8192, 3):
+            assert r[32 * i:32 * i + 32] == O.fq_op(op, ab[32 * i:32 * i + 32], bb[32 * i:32 * i + 32])[1]
+    for op in (3, 4):
+        r, st = E.fq_op_batch(op, ab[:32 * 512])
+        for i in range(512):
+            est, e = O.fq_op(op, ab[32 * i:32 * i + 32])
+            assert st[i] == est and (est != 0 or r[32 * i:32 * i + 32] == e)
+    # x >= q is rejected like Fq::from_slice
+    r, st = E.fq_op_batch(0, be(Q), be(1))
+    assert st[0] == O.NOT_MEMBER
+
+
+def test_fq12_ops(E):
+    rng = random.Random(2)
+    n = 64
+    a = b"".join(be(rng.randrange(Q)) for _ in range(12 * n))
+    b = b"".join(be(rng.randrange(Q)) for _ in range(12 * n))
+    for op in range(8):
+        r, st = E.fq12_op_batch(op, a, b)
+        assert not any(st)
+        for i in range(n):
+            assert r[384 * i:384 * (i + 1)] == O.fq12_op(op, a[384 * i:384 * (i + 1)], b[384 * i:384 * (i + 1)])[1], (op, i)
+
+
+# ---------------------------------------------------------------------------------------------- hash to G1
+def test_hash_to_g1_kats(E):  # /root/reference/src/hash_test.rs:9-30
+    for v in G["hash_to_g1"]:
+        m = H(v["msg"])
+        out, st = E.hash_to_g1_batch(m, len(m), 1)
+        assert st[0] == 0
+        c, cst = E.g1_compress_batch(out)
+        assert cst[0] == 0 and c == H(v["compressed"])
+
+
+def test_hash_to_g1_random_fixed_len(E):
+    n = 8192
+    msgs = synth.messages(n, 32, seed=1)
+    out, st = E.hash_to_g1_batch(msgs, 32, n)
+    eout, est = O.hash_to_g1_batch(msgs, 32, n, NTHREADS)
+    assert st == est and out == eout
+
+
+def test_hash_to_g1_ragged(E):
+    rng = random.Random(3)
+    lens = [0, 1, 3, 31, 32, 33, 54, 55, 56, 62, 63, 64, 65, 118, 119, 120, 127, 128, 129, 300, 1000]
+    msgs = [rng.randbytes(rng.choice(lens)) for _ in range(600)] + [b""]
+    out, st, tries = E.hash_to_g1_var(msgs)
+    for i, m in enumerate(msgs):
+        est, e, ectr = O.hash_to_g1(m)
+        assert (st[i], out[64 * i:64 * i + 64], tries[i]) == (est, e, ectr), i
+    assert max(tries) >= 3  # the retry loop really ran
+
+
+# ---------------------------------------------------------------------------------------------- sign / keys
+def test_sign_kat(E):  # /root/reference/src/ecdsa_test.rs:5-17
+    for v in G["sign"]:
+        m = H(v["msg"])
+        sig, st = E.sign_batch(m, len(m), H(v["sk"]))
+        assert st[0] == 0
+        assert E.g1_compress_batch(sig)[0] == H(v["sig_compressed"])
+
+
+def test_sign_random(E):
+    n = 2048
+    msgs, sks = synth.messages(n, 32, seed=11), synth.rand_bytes(12, 32 * n)  # arbitrary 32-byte keys, many >= r
+    sig, st = E.sign_batch(msgs, 32, sks)
+    esig, est = O.sign_batch(msgs, 32, sks, n, NTHREADS)
+    assert st == est and sig == esig
+
+
+def test_sk_to_pk_kats(E):  # /root/reference/src/types_test.rs:71-129 + the example's keys (> r)
+    for v in G["sk_to_pk_g2"]:
+        assert E.derive_pk_g2_batch(H(v["sk"])) == H(v["pk_uncompressed"])
+    sks = b"".join(H(s) for s in G["example"]["sks"]) + synth.rand_bytes(21, 32 * 254)
+    n = len(sks) // 32
+    assert E.derive_pk_g2_batch(sks) == O.derive_pk_g2_batch(sks, n, NTHREADS)
+    assert E.derive_pk_g1_batch(sks) == O.derive_pk_g1_batch(sks, n, NTHREADS)
+
+
+def test_bn256_json(E):  # /root/reference/src/bn256.json
+    for v in G["bn256_json"]["add"]:
+        r, st = E.g1_sum(H(v["x1"]) + H(v["y1"]) + H(v["x2"]) + H(v["y2"]))
+        assert st == 0 and r == H(v["result"])
+    pts = b"".join(H(v["x"]) + H(v["y"]) for v in G["bn256_json"]["mul"])
+    ks = b"".join(H(v["scalar"]) for v in G["bn256_json"]["mul"])
+    r, st = E.g1_mul_batch(pts, ks)
+    assert not any(st)
+    for i, v in enumerate(G["bn256_json"]["mul"]):
+        assert r[64 * i:64 * i + 64] == H(v["result"])
+
+
+# ---------------------------------------------------------------------------------------------- verify
+def _signed_set(E, n, seed):
+    msgs, sks = synth.messages(n, 32, seed=seed), synth.secret_keys(n, seed=seed + 1)
+    sigs, st = E.sign_batch(msgs, 32, sks)
+    assert not any(st)
+    pks = E.derive_pk_g2_batch(sks)
+    return msgs, sks, sigs, pks
+
+
+def test_verify_batch_with_adversarial_items(E):
+    n = 1024
+    msgs, sks, sigs, pks = _signed_set(E, n, seed=31)
+    msgs, sigs, pks = bytearray(msgs), bytearray(sigs), bytearray(pks)
+    rng = random.Random(7)
+    kinds = {}
+    for i in rng.sample(range(n), 200):
+        kind = rng.randrange(8)
+        kinds[i] = kind
+        if kind == 0:  # wrong message
+            msgs[32 * i] ^= 1
+        elif kind == 1:  # negated signature
+            sigs[64 * i:64 * i + 64] = O.g1_neg(bytes(sigs[64 * i:64 * i + 64]))[1]
+        elif kind == 2:  # key of another signer
+            j = (i + 1) % n
+            pks[128 * i:128 * i + 128] = pks[128 * j:128 * j + 128]
+        elif kind == 3:  # sig + G1
+            sigs[64 * i:64 * i + 64] = O.g1_add(bytes(sigs[64 * i:64 * i + 64]), G1_GEN)[1]
+        elif kind == 4:  # signature at infinity, real key -> reject
+            sigs[64 * i:64 * i + 64] = bytes(64)
+        elif kind == 5:  # both at infinity -> both pairs skipped -> accept (dependency semantics)
+            sigs[64 * i:64 * i + 64] = bytes(64)
+            pks[128 * i:128 * i + 128] = bytes(128)
+        elif kind == 6:  # off-curve signature
+            sigs[64 * i + 63] ^= 1
+        elif kind == 7:  # coordinate >= q
+            sigs[64 * i:64 * i + 32] = be(Q + 5)
+    msgs, sigs, pks = bytes(msgs), bytes(sigs), bytes(pks)
+    st = E.verify_batch(msgs, 32, sigs, pks)
+    est = O.verify_batch(msgs, 32, sigs, pks, n, NTHREADS)
+    assert st == est
+    assert sum(1 for s in st if s == 0) >= n - 200 and O.VERIFICATION_FAILED in st and O.INVALID_GROUP_POINT in st and O.NOT_MEMBER in st
+    for i, k in kinds.items():
+        assert (st[i] == 0) == (k == 5), (i, k)
+
+
+def test_miller_and_final_exp_layers(E):
+    n = 64
+    msgs, sks, sigs, pks = _signed_set(E, n, seed=41)
+    hs, _ = E.hash_to_g1_batch(msgs, 32, n)
+    neg_g2 = O.g2_neg(O.derive_pk_g2(be(1))[1])[1]
+    g1s = b"".join(hs[64 * i:64 * i + 64] + sigs[64 * i:64 * i + 64] for i in range(n))
+    g2s = b"".join(pks[128 * i:128 * i + 128] + neg_g2 for i in range(n))
+    f, st = E.miller_loop_batch(g1s, g2s, 2, n)
+    assert not any(st)
+    for i in range(n):
+        assert f[384 * i:384 * i + 384] == O.miller_product(g1s[128 * i:128 * i + 128], g2s[256 * i:256 * i + 256], 2)[1]
+    gt, st = E.final_exp_batch(f)
+    one = be(1) + bytes(352)
+    for i in range(n):
+        assert st[i] == 0 and gt[384 * i:384 * i + 384] == one
+    rnd = b"".join(be(random.Random(i).randrange(Q)) for i in range(12 * 16))
+    gt, st = E.final_exp_batch(rnd)
+    for i in range(16):
+        assert gt[384 * i:384 * i + 384] == O.final_exp(rnd[384 * i:384 * i + 384])[1]
+    assert E.pairing_check_batch(g1s, g2s, 2, n) == bytes(n)
+    # a product with a skipped (infinite) pair and k = 0
+    assert E.pairing_check_batch(g1s[:128] + bytes(64), g2s[:256] + neg_g2, 3, 1) == b"\x00"
+    assert E.pairing_check_batch(b"", b"", 0, 3) == bytes(3)
+
+
+def test_reference_api_vectors(E):
+    """The reference's own tests, restated against the API mirror (src/ecdsa_test.rs, src/types_test.rs, examples/bn254.rs)."""
+    from bn254_b200 import ECDSA, Error, PrivateKey, PublicKey, PublicKeyG1, Signature, check_public_keys
+    v = G["verify_ok"][0]
+    sk = PrivateKey(H(v["sk"]))
+    pk = PublicKey.from_private_key(sk)
+    sig = Signature.from_compressed(H(v["sig_compressed"]))
+    assert ECDSA.verify(H(v["msg"]), sig, pk) is None
+    assert ECDSA.sign(H(v["msg"]), sk).to_compressed() == H(v["sig_compressed"])
+    # aggregate of two signers (src/ecdsa_test.rs:41-79) and the example (keys > r)
+    for v in G["aggregate_verify_ok"] + [G["example"]]:
+        msg = H(v["msg"])
+        sks = [PrivateKey(H(s)) for s in v["sks"]]
+        pks = [PublicKey.from_private_key(s) for s in sks]
+        sigs = [ECDSA.sign(msg, s) for s in sks]
+        assert ECDSA.verify(msg, sigs[0] + sigs[1], pks[0] + pks[1]) is None
+        with pytest.raises(Error) as e:
+            ECDSA.verify(msg, sigs[0], pks[0] + pks[1])
+        assert e.value.variant == "VerificationFailed"
+        # Sub / Neg: (s0 + s1) - s1 == s0 ; -(-s0) == s0
+        assert ((sigs[0] + sigs[1]) - sigs[1]).raw == sigs[0].raw and (-(-sigs[0])).raw == sigs[0].raw
+        assert ((pks[0] + pks[1]) - pks[1]).raw == pks[0].raw
+    ex = G["example"]
+    sks = [PrivateKey(H(s)) for s in ex["sks"]]
+    agg_sig = ECDSA.sign(H(ex["msg"]), sks[0]) + ECDSA.sign(H(ex["msg"]), sks[1])
+    agg_pk = PublicKey.from_private_key(sks[0]) + PublicKey.from_private_key(sks[1])
+    assert agg_sig.to_compressed().hex() == "020aea1d3390792923eb34734b1669efad8a388997061c42fb9f7d310eec339ada"
+    assert agg_pk.to_compressed().hex() == (
+        "0a08685b8899122e2d7da466f39d7698b3918cf3e7ae2a2d8a3cbb6713ee4238c7e3fbfc289492c9c6b70f01a86182add29428b2ce4a6ec6ba67603ee22d7670ec")
+    # check_public_keys accept / reject (src/ecdsa_test.rs:82-112)
+    v = G["check_public_keys_ok"][0]
+    s = PrivateKey(H(v["sk"]))
+    assert check_public_keys(PublicKey.from_private_key(s), PublicKeyG1.from_private_key(s)) is None
+    v = G["check_public_keys_fail"][0]
+    with pytest.raises(Error) as e:
+        check_public_keys(PublicKey.from_private_key(PrivateKey(H(v["sk_g2"]))), PublicKeyG1.from_private_key(PrivateKey(H(v["sk_g1"]))))
+    assert e.value.variant == "VerificationFailed"
+    # uncompressed round trips through verify (src/ecdsa_test.rs:115-154)
+    v = G["sig_uncompressed_roundtrip"][0]
+    sig = Signature.from_compressed(H(v["sig_compressed"]))
+    sig2 = Signature.from_uncompressed(sig.to_uncompressed())
+    assert ECDSA.verify(H(v["msg"]), sig2, PublicKey.from_private_key(PrivateKey(H(v["sk"])))) is None
+    # G2 codecs (src/types_test.rs:48-69) and generator sums (:132-159)
+    c = H(G["g2_compressed_roundtrip"][0]["compressed"])
+    assert PublicKey.from_compressed(c).to_compressed() == c
+    u = H(G["g2_uncompressed_roundtrip"][0]["uncompressed"])
+    assert PublicKey.from_uncompressed(u).to_uncompressed() == u
+    one = PrivateKey(be(1))
+    g2, g1 = PublicKey.from_private_key(one), PublicKeyG1.from_private_key(one)
+    assert (g2 + g2).to_compressed() == H(G["g2_gen_plus_gen_compressed"])
+    assert (g1 + g1).to_compressed() == H(G["g1_gen_plus_gen_compressed"])
+    # serde forms
+    assert PublicKey.deserialize(g2.serialize()).raw == g2.raw and len(g2.serialize()) == 65
+    # infinity cannot be serialised (PointInJacobian)
+    with pytest.raises(Error) as e:
+        (g1 - g1).to_compressed()
+    assert e.value.variant == "PointInJacobian"
+
+
+# ---------------------------------------------------------------------------------------------- codecs
+def test_codecs(E):
+    n = 256
+    sks = synth.secret_keys(n, seed=51)
+    p1, p2 = E.derive_pk_g1_batch(sks), E.derive_pk_g2_batch(sks)
+    c1, st = E.g1_compress_batch(p1)
+    assert not any(st)
+    c2, st = E.g2_compress_batch(p2[:128 * 32])
+    assert not any(st)
+    for i in range(n):
+        assert c1[33 * i:33 * i + 33] == O.g1_compress(p1[64 * i:64 * i + 64])[1]
+    for i in range(32):
+        assert c2[65 * i:65 * i + 65] == O.g2_compress(p2[128 * i:128 * i + 128])[1]
+    d1, st = E.g1_decompress_batch(c1)
+    assert not any(st) and d1 == p1
+    d2, st = E.g2_decompress_batch(c2)
+    assert not any(st) and d2 == p2[:128 * 32]
+    assert E.g1_validate_batch(p1) == bytes(n) and E.g2_validate_batch(p2[:128 * 16]) == bytes(16)
+    # rejection paths
+    rng = random.Random(9)
+    bad = b"".join(bytes([rng.choice([2, 3, 4])]) + be(rng.randrange(Q + 1000)) for _ in range(64))
+    out, st = E.g1_decompress_batch(bad)
+    for i in range(64):
+        est, e = O.g1_decompress(bad[33 * i:33 * i + 33])
+        assert st[i] == est and out[64 * i:64 * i + 64] == e
+    flip = bytes([c2[0] ^ 1]) + c2[1:65]
+    assert E.g2_decompress_batch(flip)[0] == O.g2_neg(p2[:128])[1]
+    assert E.g2_decompress_batch(b"\x0c" + c2[1:65])[1][0] == O.INVALID_ENCODING
+    assert E.g1_validate_batch(be(1) + be(3))[0] == O.INVALID_GROUP_POINT
+    assert E.g1_compress_batch(bytes(64))[1][0] == O.POINT_IN_JACOBIAN
+    # twist point outside the r-torsion is rejected by the subgroup check
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle as P
+    x = 1
+    while True:
+        y = P.f2_sqrt(P.f2_add(P.f2_mul(P.f2_mul((x, 0), (x, 0)), (x, 0)), P.B2))
+        if y is not None and not P.g2_in_subgroup(((x, 0), y)):
+            break
+        x += 1
+    raw = be(x) + be(0) + be(y[0]) + be(y[1])
+    assert E.g2_validate_batch(raw)[0] == O.INVALID_GROUP_POINT
+
+
+# ---------------------------------------------------------------------------------------------- aggregation
+def test_sums_vs_oracle(E):
+    n = 5000  # ragged: not a multiple of the block size
+    sks = synth.secret_keys(n, seed=61)
+    p1, p2 = E.derive_pk_g1_batch(sks), E.derive_pk_g2_batch(sks[:32 * 700])
+    assert E.g1_sum(p1) == (O.g1_sum(p1, n)[1], 0)
+    assert E.g2_sum(p2) == (O.g2_sum(p2, 700)[1], 0)
+    assert E.g1_sum(b"") == (bytes(64), 0) and E.g2_sum(b"") == (bytes(128), 0)
+    # duplicates (doubling inside the tree), infinities, P + (-P)
+    d = p1[:64] * 9 + bytes(64) + p1[64:128]
+    assert E.g1_sum(d) == (O.g1_sum(d, 11)[1], 0)
+    assert E.g1_sum(p1[:64] + O.g1_neg(p1[:64])[1]) == (bytes(64), 0)
+    assert E.g1_sum(p1[:128], bytes([0, 1])) == (O.g1_add(p1[:64], O.g1_neg(p1[64:128])[1])[1], 0)
+    # an invalid point is reported with the status of the first failing item
+    bad = p1[:640] + be(1) + be(3) + p1[640:1280]
+    assert E.g1_sum(bad)[1] == O.INVALID_GROUP_POINT
+
+
+def test_aggregate_verify_same_message(E):
+    n = 3000
+    msg = b"same message for everyone"
+    sks = synth.secret_keys(n, seed=71)
+    sigs, st = E.sign_batch(msg * n, len(msg), sks)
+    pks = E.derive_pk_g2_batch(sks)
+    assert E.aggregate_verify_same_msg(msg, sigs, pks) == 0
+    assert O.verify(msg, E.g1_sum(sigs)[0], E.g2_sum(pks)[0]) == 0  # the sums themselves verify under the oracle
+    assert E.aggregate_verify_same_msg(msg, sigs[64:], pks) == O.VERIFICATION_FAILED
+    assert E.aggregate_verify_same_msg(msg + b"!", sigs, pks) == O.VERIFICATION_FAILED
+
+
+def test_aggregate_verify_distinct_messages(E):
+    n = 1500
+    msgs, sks, sigs, pks = _signed_set(E, n, seed=81)
+    agg = E.g1_sum(sigs)[0]
+    assert E.aggregate_verify_distinct(msgs, 32, pks, agg) == 0
+    assert E.aggregate_verify_distinct(msgs, 32, pks, E.g1_sum(sigs[64:])[0]) == O.VERIFICATION_FAILED
+    # sharded the way bench.py shards across GPUs: partial Miller products, then one shared final exponentiation
+    cuts = [0, 400, 401, 1100, n]
+    parts = b"".join(E.miller_partial_distinct(msgs[32 * a:32 * b], 32, pks[128 * a:128 * b])[0] for a, b in zip(cuts, cuts[1:]))
+    assert E.finish_distinct(parts, agg) == 0
+    # the partial of a small slice equals the oracle's Miller product (field elements are canonical)
+    hs, _ = E.hash_to_g1_batch(msgs, 32, 8)
+    assert E.miller_partial_distinct(msgs[:256], 32, pks[:1024])[0] == O.miller_product(hs, pks[:1024], 8)[1]
+    assert E.miller_partial_distinct(b"", 32, b"") == (be(1) + bytes(352), 0)
+
+
+# ---------------------------------------------------------------------------------------------- full BASELINE sizes
+def test_full_size_verify_2_20(E):
+    """configs[1]: 2^20 independent triples; 1 % flipped invalid (seeded).  The verdict vector must equal the
+    construction (valid -> 0, flipped -> 9) and, on a 2^12 sample, the oracle's."""
+    n = 1 << 20
+    msgs, sks, sigs, pks = _signed_set(E, n, seed=1)
+    rng = np.random.default_rng(99)
+    bad = np.sort(rng.choice(n, size=n // 100, replace=False))
+    m = np.frombuffer(msgs, dtype=np.uint8).reshape(n, 32).copy()
+    m[bad, 5] ^= 0x40
+    msgs = m.tobytes()
+    st = np.frombuffer(E.verify_batch(msgs, 32, sigs, pks), dtype=np.uint8)
+    expect = np.zeros(n, dtype=np.uint8)
+    expect[bad] = O.VERIFICATION_FAILED
+    assert np.array_equal(st, expect)
+    idx = np.concatenate([bad[:2048], np.arange(2048)])
+    sm = b"".join(msgs[32 * i:32 * i + 32] for i in idx)
+    ss = b"".join(sigs[64 * i:64 * i + 64] for i in idx)
+    sp = b"".join(pks[128 * i:128 * i + 128] for i in idx)
+    assert O.verify_batch(sm, 32, ss, sp, len(idx), NTHREADS) == bytes(st[idx])
+
+
+def test_full_size_sums_linearity(E):
+    """configs[3] at 2^20: sum(k_i * G) == (sum k_i) * G for G1 and G2, and the aggregate verifies."""
+    n = 1 << 20
+    sks = synth.secret_keys(n, seed=2)
+    total = sum(int.from_bytes(sks[32 * i:32 * i + 32], "big") for i in range(n)) % R
+    p1 = E.derive_pk_g1_batch(sks)
+    assert E.g1_sum(p1) == (O.derive_pk_g1(be(total))[1], 0)
+    p2 = E.derive_pk_g2_batch(sks)
+    assert E.g2_sum(p2) == (O.derive_pk_g2(be(total))[1], 0)
+    msg = synth.messages(1, 32, seed=3)
+    sigs, st = E.sign_batch(msg * n, 32, sks)
+    assert E.aggregate_verify_same_msg(msg, sigs, p2) == 0
+    assert E.g1_sum(sigs)[0] == O.sign(msg, be(total))[1]
