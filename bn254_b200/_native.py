@@ -19,7 +19,7 @@ SYMBOLS = [
     "bn254_g1_validate_batch", "bn254_g2_validate_batch",
     "bn254_aggregate_verify_same_msg", "bn254_aggregate_verify_distinct",
     "bn254_miller_partial_distinct", "bn254_miller_partial_distinct_dev", "bn254_finish_distinct",
-    "bn254_miller_loop_batch", "bn254_final_exp_batch", "bn254_fq_op_batch", "bn254_fq12_op_batch",
+    "bn254_miller_loop_batch", "bn254_final_exp_batch", "bn254_fq_op_batch", "bn254_fq12_op_batch", "bn254_layer_op_batch",
 ]
 
 _lib = None

@@ -190,6 +190,18 @@ __global__ void __launch_bounds__(BN_BLOCK) k_fq12_op(int op, const uint8_t* __r
   }
 }
 
+// layer hook: n_in Fq values in, n_out Fq values out per item (see debug_layer_op)
+__global__ void __launch_bounds__(BN_BLOCK) k_layer_op(int op, const uint8_t* __restrict__ in, int n_in, size_t n, uint8_t* __restrict__ out,
+                                                       int n_out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  fq a[20], r[12];
+  for (int k = 0; k < 12; k++) r[k] = fq_zero();
+  for (int k = 0; k < n_in && k < 20; k++) fq_from_be(&a[k], in + 32 * ((size_t)n_in * i + k));
+  debug_layer_op(op, a, r);
+  for (int k = 0; k < n_out && k < 12; k++) fq_to_be(out + 32 * ((size_t)n_out * i + k), r[k]);
+}
+
 // generic per-item map kernel for the light-weight entry points (codecs, key derivation, scalar multiplication)
 enum { OP_G1_MUL, OP_G2_MUL, OP_DERIVE_G1, OP_DERIVE_G2, OP_G1_COMPRESS, OP_G1_DECOMPRESS, OP_G2_COMPRESS, OP_G2_DECOMPRESS, OP_G1_VALIDATE, OP_G2_VALIDATE };
 template <int OP>
@@ -362,7 +374,8 @@ __global__ void k_distinct_finish(const uint8_t* __restrict__ partials_be, int m
     return;
   }
   if (!pt_is_inf(&s)) {
-    miller_loop_2(&t, false, &s.x, &s.y, (const fq2*)0, (const fq2*)0, true, &s.x, &s.y, lines);
+    fq2 dummy = fq2_one();
+    miller_loop_2(&t, false, &s.x, &s.y, &dummy, &dummy, true, &s.x, &s.y, lines);
     fq12_mul(&acc, &acc, &t);
   }
   *status = item_final_exp_is_one(&acc);
@@ -740,6 +753,18 @@ int bn254_fq_op_batch(bn254_ctx* ctx, int op, const uint8_t* a32, const uint8_t*
   LAUNCH(k_fq_op, grid_for(n), BN_BLOCK, op, d_a.as<uint8_t>(), d_b.as<uint8_t>(), n, d_out.as<uint8_t>(), d_st.as<uint8_t>());
   D2H(out32, d_out.p, 32 * n);
   D2H(status, d_st.p, n);
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int bn254_layer_op_batch(bn254_ctx* ctx, int op, const uint8_t* in, size_t n_in, size_t n, uint8_t* out, size_t n_out) {
+  ENTER();
+  if (n == 0) return 0;
+  ARGCHECK(in && out && n_in <= 20 && n_out <= 12);
+  DALLOC(d_in, 32 * n_in * n);
+  DALLOC(d_out, 32 * n_out * n);
+  H2D(d_in.p, in, 32 * n_in * n);
+  LAUNCH(k_layer_op, grid_for(n), BN_BLOCK, op, d_in.as<uint8_t>(), (int)n_in, n, d_out.as<uint8_t>(), (int)n_out);
+  D2H(out, d_out.p, 32 * n_out * n);
   CK(cudaStreamSynchronize(ctx->stream));
   return 0;
 }

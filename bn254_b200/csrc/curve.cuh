@@ -15,16 +15,8 @@ BN_FN fq fe_add(const fq& a, const fq& b) { return fq_add(a, b); }
 BN_FN fq fe_sub(const fq& a, const fq& b) { return fq_sub(a, b); }
 BN_FN fq fe_dbl(const fq& a) { return fq_dbl(a); }
 BN_FN fq fe_neg(const fq& a) { return fq_neg(a); }
-BN_FN fq fe_mul(const fq& a, const fq& b) {
-  fq r;
-  fq_mul_ni(&r, &a, &b);
-  return r;
-}
-BN_FN fq fe_sqr(const fq& a) {
-  fq r;
-  fq_mul_ni(&r, &a, &a);
-  return r;
-}
+BN_FN fq fe_mul(const fq& a, const fq& b) { return fq_mul(a, b); }
+BN_FN fq fe_sqr(const fq& a) { return fq_sqr(a); }
 BN_FN bool fe_is_zero(const fq& a) { return fq_is_zero(a); }
 BN_FN bool fe_eq(const fq& a, const fq& b) { return fq_eq(a, b); }
 BN_FN void fe_set_one(fq* a) { *a = fq_one(); }
@@ -41,7 +33,7 @@ BN_FN bool fe_is_zero(const fq2& a) { return fq2_is_zero(a); }
 BN_FN bool fe_eq(const fq2& a, const fq2& b) { return fq2_eq(a, b); }
 BN_FN void fe_set_one(fq2* a) { *a = fq2_one(); }
 BN_FN void fe_set_zero(fq2* a) { *a = fq2_zero(); }
-BN_FN fq2 fe_inv(const fq2& a) {
+BN_FN fq2 fe_inv(fq2 a) {
   fq2 r;
   fq2_inv(&r, &a);
   return r;

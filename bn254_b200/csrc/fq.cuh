@@ -99,7 +99,7 @@ BN_FN fq fq_add(const fq& a, const fq& b) {
       "addc.cc.u32 %5, %13, %21;\n\t"
       "addc.cc.u32 %6, %14, %22;\n\t"
       "addc.u32 %7, %15, %23;\n\t"
-      : "=r"(s0), "=r"(s1), "=r"(s2), "=r"(s3), "=r"(s4), "=r"(s5), "=r"(s6), "=r"(s7)
+      : "=&r"(s0), "=&r"(s1), "=&r"(s2), "=&r"(s3), "=&r"(s4), "=&r"(s5), "=&r"(s6), "=&r"(s7)
       : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]),
         "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
   asm("sub.cc.u32 %0, %9, 0xd87cfd47;\n\t"
@@ -111,7 +111,7 @@ BN_FN fq fq_add(const fq& a, const fq& b) {
       "subc.cc.u32 %6, %15, 0xe131a029;\n\t"
       "subc.cc.u32 %7, %16, 0x30644e72;\n\t"
       "subc.u32 %8, 0, 0;\n\t"
-      : "=r"(t0), "=r"(t1), "=r"(t2), "=r"(t3), "=r"(t4), "=r"(t5), "=r"(t6), "=r"(t7), "=r"(bw)
+      : "=&r"(t0), "=&r"(t1), "=&r"(t2), "=&r"(t3), "=&r"(t4), "=&r"(t5), "=&r"(t6), "=&r"(t7), "=&r"(bw)
       : "r"(s0), "r"(s1), "r"(s2), "r"(s3), "r"(s4), "r"(s5), "r"(s6), "r"(s7));
   fq r;
   bool keep = bw != 0;  // borrow: a + b < q
@@ -130,7 +130,7 @@ BN_FN fq fq_sub(const fq& a, const fq& b) {
       "subc.cc.u32 %6, %15, %23;\n\t"
       "subc.cc.u32 %7, %16, %24;\n\t"
       "subc.u32 %8, 0, 0;\n\t"
-      : "=r"(d0), "=r"(d1), "=r"(d2), "=r"(d3), "=r"(d4), "=r"(d5), "=r"(d6), "=r"(d7), "=r"(m)
+      : "=&r"(d0), "=&r"(d1), "=&r"(d2), "=&r"(d3), "=&r"(d4), "=&r"(d5), "=&r"(d6), "=&r"(d7), "=&r"(m)
       : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]),
         "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
   fq r;
@@ -142,7 +142,7 @@ BN_FN fq fq_sub(const fq& a, const fq& b) {
       "addc.cc.u32 %5, %13, %21;\n\t"
       "addc.cc.u32 %6, %14, %22;\n\t"
       "addc.u32 %7, %15, %23;\n\t"
-      : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7])
+      : "=&r"(r.l[0]), "=&r"(r.l[1]), "=&r"(r.l[2]), "=&r"(r.l[3]), "=&r"(r.l[4]), "=&r"(r.l[5]), "=&r"(r.l[6]), "=&r"(r.l[7])
       : "r"(d0), "r"(d1), "r"(d2), "r"(d3), "r"(d4), "r"(d5), "r"(d6), "r"(d7),
         "r"(m & BN_Q0), "r"(m & BN_Q1), "r"(m & BN_Q2), "r"(m & BN_Q3), "r"(m & BN_Q4), "r"(m & BN_Q5), "r"(m & BN_Q6), "r"(m & BN_Q7));
   return r;
@@ -232,7 +232,7 @@ BN_FN void mont_row_first(uint32_t* Y, uint32_t* X, const uint32_t* a, uint32_t 
       "mul.hi.u32 %5, %10, %12;\n\t"
       "mul.lo.u32 %6, %11, %12;\n\t"
       "mul.hi.u32 %7, %11, %12;\n\t"
-      : "=r"(Y[0]), "=r"(Y[1]), "=r"(Y[2]), "=r"(Y[3]), "=r"(Y[4]), "=r"(Y[5]), "=r"(Y[6]), "=r"(Y[7])
+      : "=&r"(Y[0]), "=&r"(Y[1]), "=&r"(Y[2]), "=&r"(Y[3]), "=&r"(Y[4]), "=&r"(Y[5]), "=&r"(Y[6]), "=&r"(Y[7])
       : "r"(a[0]), "r"(a[2]), "r"(a[4]), "r"(a[6]), "r"(w));
   asm("mul.lo.u32 %0, %8, %12;\n\t"
       "mul.hi.u32 %1, %8, %12;\n\t"
@@ -242,7 +242,7 @@ BN_FN void mont_row_first(uint32_t* Y, uint32_t* X, const uint32_t* a, uint32_t 
       "mul.hi.u32 %5, %10, %12;\n\t"
       "mul.lo.u32 %6, %11, %12;\n\t"
       "mul.hi.u32 %7, %11, %12;\n\t"
-      : "=r"(X[0]), "=r"(X[1]), "=r"(X[2]), "=r"(X[3]), "=r"(X[4]), "=r"(X[5]), "=r"(X[6]), "=r"(X[7])
+      : "=&r"(X[0]), "=&r"(X[1]), "=&r"(X[2]), "=&r"(X[3]), "=&r"(X[4]), "=&r"(X[5]), "=&r"(X[6]), "=&r"(X[7])
       : "r"(a[1]), "r"(a[3]), "r"(a[5]), "r"(a[7]), "r"(w));
 }
 // later rows: Y is the accumulator aligned at the new base column, X is the previous base-aligned accumulator
@@ -308,7 +308,7 @@ BN_FN fq mont_finish(const uint32_t* X, const uint32_t* Y) {
       "addc.cc.u32 %5, %13, %21;\n\t"
       "addc.cc.u32 %6, %14, %22;\n\t"
       "addc.u32 %7, %15, 0;\n\t"
-      : "=r"(s0), "=r"(s1), "=r"(s2), "=r"(s3), "=r"(s4), "=r"(s5), "=r"(s6), "=r"(s7)
+      : "=&r"(s0), "=&r"(s1), "=&r"(s2), "=&r"(s3), "=&r"(s4), "=&r"(s5), "=&r"(s6), "=&r"(s7)
       : "r"(X[0]), "r"(X[1]), "r"(X[2]), "r"(X[3]), "r"(X[4]), "r"(X[5]), "r"(X[6]), "r"(X[7]),
         "r"(Y[1]), "r"(Y[2]), "r"(Y[3]), "r"(Y[4]), "r"(Y[5]), "r"(Y[6]), "r"(Y[7]));
   asm("sub.cc.u32 %0, %9, 0xd87cfd47;\n\t"
@@ -320,7 +320,7 @@ BN_FN fq mont_finish(const uint32_t* X, const uint32_t* Y) {
       "subc.cc.u32 %6, %15, 0xe131a029;\n\t"
       "subc.cc.u32 %7, %16, 0x30644e72;\n\t"
       "subc.u32 %8, 0, 0;\n\t"
-      : "=r"(t0), "=r"(t1), "=r"(t2), "=r"(t3), "=r"(t4), "=r"(t5), "=r"(t6), "=r"(t7), "=r"(bw)
+      : "=&r"(t0), "=&r"(t1), "=&r"(t2), "=&r"(t3), "=&r"(t4), "=&r"(t5), "=&r"(t6), "=&r"(t7), "=&r"(bw)
       : "r"(s0), "r"(s1), "r"(s2), "r"(s3), "r"(s4), "r"(s5), "r"(s6), "r"(s7));
   fq r;
   bool keep = bw != 0;

@@ -303,3 +303,65 @@ BN_FN int item_g2_decompress(uint8_t* out, const uint8_t* in) {
 }
 
 }  // namespace bn
+
+// ---------------------------------------------------------------------------------------------- layer hooks
+// Building blocks exposed to the parity tests (GPU kernel vs g++ host simulation vs oracle), Fq arrays in / out:
+//   op 0 fq2_mul (4 -> 2), 1 fq2_sqr (2 -> 2), 2 fq2_scale (3 -> 2), 3 doubling_step (6 -> 12),
+//   4 mixed_addition_step (q:4, r:6 -> 12), 5 fq12_mul_by_024 (12 + 6 -> 12), 6 G1 pt_madd (jac 3 + affine 2 -> 3),
+//   7 fq2_mul_xi (2 -> 2), 8 fq2_inv (2 -> 2), 11 G1 pt_madd in place, 12 G1 pt_add (6 -> 3), 13 G2 pt_madd (10 -> 6),
+//   200 single-pair Miller loop (p:2, q:4 -> 12)
+namespace bn {
+BN_FN void debug_layer_op(int op, const fq* in, fq* out) {
+  const fq2* i2 = (const fq2*)in;
+  fq2* o2 = (fq2*)out;
+  if (op == 0) fq2_mul(&o2[0], &i2[0], &i2[1]);
+  else if (op == 1) fq2_sqr(&o2[0], &i2[0]);
+  else if (op == 2) fq2_scale(&o2[0], &i2[0], &in[2]);
+  else if (op == 3) {
+    g2proj r;
+    line_t c;
+    r.x = i2[0]; r.y = i2[1]; r.z = i2[2];
+    doubling_step(&r, &c);
+    o2[0] = r.x; o2[1] = r.y; o2[2] = r.z; o2[3] = c.ell_0; o2[4] = c.ell_vw; o2[5] = c.ell_vv;
+  } else if (op == 4) {
+    g2proj r;
+    line_t c;
+    r.x = i2[2]; r.y = i2[3]; r.z = i2[4];
+    mixed_addition_step(&i2[0], &i2[1], &r, &c);
+    o2[0] = r.x; o2[1] = r.y; o2[2] = r.z; o2[3] = c.ell_0; o2[4] = c.ell_vw; o2[5] = c.ell_vv;
+  } else if (op == 5) {
+    fq12 f = *(const fq12*)in;
+    fq12_mul_by_024(&f, &i2[6], &i2[7], &i2[8]);
+    *(fq12*)out = f;
+  } else if (op == 6) {
+    g1j p, r;
+    p.x = in[0]; p.y = in[1]; p.z = in[2];
+    pt_madd(&r, &p, &in[3], &in[4]);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z;
+  } else if (op == 7) o2[0] = fq2_mul_xi(i2[0]);
+  else if (op == 8) fq2_inv(&o2[0], &i2[0]);
+  else if (op == 200) {
+    fq12 f;
+    miller_loop_2(&f, true, &in[0], &in[1], (const fq2*)&in[2], (const fq2*)&in[4], false, &in[0], &in[1], (const line_t*)0);
+    *(fq12*)out = f;
+  } else if (op == 11) {
+    g1j p;
+    p.x = in[0]; p.y = in[1]; p.z = in[2];
+    pt_madd(&p, &p, &in[3], &in[4]);
+    out[0] = p.x; out[1] = p.y; out[2] = p.z;
+  } else if (op == 12) {
+    g1j p, q, r;
+    p.x = in[0]; p.y = in[1]; p.z = in[2];
+    q.x = in[3]; q.y = in[4]; q.z = in[5];
+    pt_add(&r, &p, &q);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z;
+  } else if (op == 13) {
+    g2j p, r;
+    const fq2* i2b = (const fq2*)in;
+    p.x = i2b[0]; p.y = i2b[1]; p.z = i2b[2];
+    pt_madd(&r, &p, &i2b[3], &i2b[4]);
+    fq2* o = (fq2*)out;
+    o[0] = r.x; o[1] = r.y; o[2] = r.z;
+  }
+}
+}  // namespace bn

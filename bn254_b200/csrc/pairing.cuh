@@ -87,80 +87,103 @@ BN_FN void g2_frobenius_pair(fq2* q1x, fq2* q1y, fq2* q2x, fq2* q2y, const fq2& 
 }
 
 // all K_N_LINES line coefficients of a fixed affine Q (used once, for -G2)
-BN_FN void g2_precompute_lines(line_t* out, const fq2& qx, const fq2& qy) {
-  g2proj r;
-  r.x = qx;
-  r.y = qy;
-  r.z = fq2_one();
-  fq2 nqy = fq2_neg(qy);
+BN_FN void g2_precompute_lines(line_t* out, fq2 qx_in, fq2 qy_in) {
+  struct {
+    g2proj r;
+    fq2 qx, qy, nqy, q1x, q1y, q2x, q2y;
+  } L;
+  L.qx = qx_in;
+  L.qy = qy_in;
+  L.r.x = L.qx;
+  L.r.y = L.qy;
+  L.r.z = fq2_one();
+  L.nqy = fq2_neg(L.qy);
   int n = 0;
   for (int k = 0; k < 64; k++) {
-    doubling_step(&r, &out[n++]);
+    doubling_step(&L.r, &out[n++]);
     int d = K_ATE_DIGITS[k];
-    if (d == 1) mixed_addition_step(&qx, &qy, &r, &out[n++]);
-    else if (d == -1) mixed_addition_step(&qx, &nqy, &r, &out[n++]);
+    if (d == 1) mixed_addition_step(&L.qx, &L.qy, &L.r, &out[n++]);
+    else if (d == -1) mixed_addition_step(&L.qx, &L.nqy, &L.r, &out[n++]);
   }
-  fq2 q1x, q1y, q2x, q2y;
-  g2_frobenius_pair(&q1x, &q1y, &q2x, &q2y, qx, qy);
-  mixed_addition_step(&q1x, &q1y, &r, &out[n++]);
-  mixed_addition_step(&q2x, &q2y, &r, &out[n++]);
+  g2_frobenius_pair(&L.q1x, &L.q1y, &L.q2x, &L.q2y, L.qx, L.qy);
+  mixed_addition_step(&L.q1x, &L.q1y, &L.r, &out[n++]);
+  mixed_addition_step(&L.q2x, &L.q2y, &L.r, &out[n++]);
 }
 
 BN_FN void ell_apply(fq12* f, const line_t* c, const fq* px, const fq* py) {
-  fq2 vw, vv;
-  fq2_scale(&vw, &c->ell_vw, py);
-  fq2_scale(&vv, &c->ell_vv, px);
-  fq12_mul_by_024(f, &c->ell_0, &vw, &vv);
+  struct {
+    fq2 vw, vv;
+  } L;
+  fq2_scale(&L.vw, &c->ell_vw, py);
+  fq2_scale(&L.vv, &c->ell_vv, px);
+  fq12_mul_by_024(f, &c->ell_0, &L.vw, &L.vv);
 }
 
 // f = miller(Pa, Qa) * miller(Pb, fixed Q given by its line table), sharing the squaring chain.
-//   use_a / use_b: whether each pair takes part (a pair holding an infinity is skipped by the caller's flags).
+//   USE_A / USE_B: whether each pair takes part (a pair holding an infinity is skipped by the caller).
 //   (pax, pay), (qax, qay): affine G1 / G2 of the variable pair;  (pbx, pby): affine G1 paired with the table.
-BN_NOINLINE void miller_loop_2(fq12* f, bool use_a, const fq* pax, const fq* pay, const fq2* qax, const fq2* qay, bool use_b,
-                               const fq* pbx, const fq* pby, const line_t* table) {
+// The two flags are template parameters: each combination is its own straight-line schedule.
+template <bool USE_A, bool USE_B>
+BN_NOINLINE void miller_loop_t(fq12* f, const fq* pax, const fq* pay, const fq2* qax, const fq2* qay, const fq* pbx, const fq* pby,
+                               const line_t* table) {
   fq12_set_one(f);
-  if (!use_a && !use_b) return;
-  g2proj r;
-  fq2 nqy;
-  line_t c;
-  if (use_a) {
+  // Every local whose address is handed to an out-of-line routine lives in ONE frame object: this toolchain's
+  // stack-slot sharing has been seen to overlap separately declared locals that were still live (a slot reached
+  // through a pointer select, or through a reference parameter of an inlined helper), and members of a single
+  // object cannot be overlapped.
+  struct {
+    g2proj r;
+    line_t c;
+    fq2 qy_sel, q1x, q1y, q2x, q2y;
+  } L;
+  g2proj& r = L.r;
+  line_t& c = L.c;
+  if (USE_A) {
     r.x = *qax;
     r.y = *qay;
     r.z = fq2_one();
-    nqy = fq2_neg(*qay);
   }
   int idx = 0;
   for (int k = 0; k < 64; k++) {
     if (k > 0) fq12_sqr(f, f);
-    if (use_a) {
+    if (USE_A) {
       doubling_step(&r, &c);
       ell_apply(f, &c, pax, pay);
     }
-    if (use_b) ell_apply(f, &table[idx], pbx, pby);
+    if (USE_B) ell_apply(f, &table[idx], pbx, pby);
     idx++;
     int d = K_ATE_DIGITS[k];
     if (d != 0) {
-      if (use_a) {
-        mixed_addition_step(qax, d > 0 ? qay : &nqy, &r, &c);
+      if (USE_A) {
+        L.qy_sel = d > 0 ? *qay : fq2_neg(*qay);
+        mixed_addition_step(qax, &L.qy_sel, &r, &c);
         ell_apply(f, &c, pax, pay);
       }
-      if (use_b) ell_apply(f, &table[idx], pbx, pby);
+      if (USE_B) ell_apply(f, &table[idx], pbx, pby);
       idx++;
     }
   }
-  fq2 q1x, q1y, q2x, q2y;
-  if (use_a) g2_frobenius_pair(&q1x, &q1y, &q2x, &q2y, *qax, *qay);
-  if (use_a) {
-    mixed_addition_step(&q1x, &q1y, &r, &c);
+  if (USE_A) {
+    g2_frobenius_pair(&L.q1x, &L.q1y, &L.q2x, &L.q2y, *qax, *qay);
+    mixed_addition_step(&L.q1x, &L.q1y, &r, &c);
     ell_apply(f, &c, pax, pay);
-  }
-  if (use_b) ell_apply(f, &table[idx], pbx, pby);
-  idx++;
-  if (use_a) {
-    mixed_addition_step(&q2x, &q2y, &r, &c);
+    if (USE_B) ell_apply(f, &table[idx], pbx, pby);
+    idx++;
+    mixed_addition_step(&L.q2x, &L.q2y, &r, &c);
     ell_apply(f, &c, pax, pay);
+    if (USE_B) ell_apply(f, &table[idx], pbx, pby);
+  } else if (USE_B) {
+    ell_apply(f, &table[idx], pbx, pby);
+    idx++;
+    ell_apply(f, &table[idx], pbx, pby);
   }
-  if (use_b) ell_apply(f, &table[idx], pbx, pby);
+}
+BN_FN void miller_loop_2(fq12* f, bool use_a, const fq* pax, const fq* pay, const fq2* qax, const fq2* qay, bool use_b, const fq* pbx,
+                         const fq* pby, const line_t* table) {
+  if (use_a && use_b) miller_loop_t<true, true>(f, pax, pay, qax, qay, pbx, pby, table);
+  else if (use_a) miller_loop_t<true, false>(f, pax, pay, qax, qay, pbx, pby, table);
+  else if (use_b) miller_loop_t<false, true>(f, pax, pay, qax, qay, pbx, pby, table);
+  else fq12_set_one(f);
 }
 
 // f^((q^12 - 1) / r): easy part (q^6 - 1)(q^2 + 1), then the hard part with three exponentiations by u

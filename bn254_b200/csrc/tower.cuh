@@ -102,12 +102,14 @@ BN_NOINLINE void fq2_scale(fq2* r, const fq2* a, const fq* s) {
   r->c0 = fq_mul(a->c0, k);
   r->c1 = fq_mul(a->c1, k);
 }
-BN_FN fq2 fq2_mulv(const fq2& a, const fq2& b) {
+// value-returning forms: operands are copied into call-local slots (by-value parameters) so that every memory
+// temporary lives only around its own call
+BN_FN fq2 fq2_mulv(fq2 a, fq2 b) {
   fq2 r;
   fq2_mul(&r, &a, &b);
   return r;
 }
-BN_FN fq2 fq2_sqrv(const fq2& a) {
+BN_FN fq2 fq2_sqrv(fq2 a) {
   fq2 r;
   fq2_sqr(&r, &a);
   return r;

@@ -222,3 +222,11 @@ def finish_distinct(partials, agg_sig, ctx=None):
     st = out(1)
     ctx.call("bn254_finish_distinct", partials if n else None, S(n), agg_sig, st)
     return st.raw[0]
+
+
+def layer_op_batch(op, data, n_in, n_out, ctx=None):
+    ctx = ctx or context()
+    n = _n(data, 32 * n_in)
+    o = out(32 * n_out * n)
+    ctx.call("bn254_layer_op_batch", I(op), data, S(n_in), S(n), o, S(n_out))
+    return o.raw[:32 * n_out * n]

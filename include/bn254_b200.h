@@ -135,6 +135,10 @@ int bn254_fq_op_batch(bn254_ctx*, int op, const uint8_t* a32, const uint8_t* b32
 /* Fq12 self-test hook: op 0 mul, 1 sqr, 2 inv, 3 cyclotomic sqr, 4..6 frobenius 1..3, 7 conj */
 int bn254_fq12_op_batch(bn254_ctx*, int op, const uint8_t* a384, const uint8_t* b384, size_t n, uint8_t* out384, uint8_t* status);
 
+/* layer hook for the parity tests: n_in Fq values in, n_out Fq values out per item; ops listed at debug_layer_op in
+ * bn254_b200/csrc/items.cuh (Fq2 product / square / scale, Miller doubling and addition steps, sparse line product, G1 mixed add) */
+int bn254_layer_op_batch(bn254_ctx*, int op, const uint8_t* in, size_t n_in, size_t n, uint8_t* out, size_t n_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -158,3 +158,11 @@ API int hs_g2_decompress(const uint8_t* in, size_t len, uint8_t* out) {
 }
 API int hs_g1_validate(const uint8_t* raw, size_t len) { return len == 64 ? item_g1_validate(raw) : ST_INVALID_LENGTH; }
 API int hs_g2_validate(const uint8_t* raw, size_t len) { return len == 128 ? item_g2_validate(raw) : ST_INVALID_LENGTH; }
+API int hs_layer_op(int op, const uint8_t* in, int n_in, uint8_t* out, int n_out) {
+  fq a[20], r[12];
+  for (int k = 0; k < 12; k++) r[k] = fq_zero();
+  for (int k = 0; k < n_in && k < 20; k++) fq_from_be(&a[k], in + 32 * k);
+  debug_layer_op(op, a, r);
+  for (int k = 0; k < n_out && k < 12; k++) fq_to_be(out + 32 * k, r[k]);
+  return 0;
+}

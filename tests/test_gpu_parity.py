@@ -403,3 +403,27 @@ def test_full_size_sums_linearity(E):
     sigs, st = E.sign_batch(msg * n, 32, sks)
     assert E.aggregate_verify_same_msg(msg, sigs, p2) == 0
     assert E.g1_sum(sigs)[0] == O.sign(msg, be(total))[1]
+
+
+# ---------------------------------------------------------------------------------------------- building blocks
+def test_layer_hooks_match_host_simulation(E):
+    """Every out-of-line building block of the pairing / group code, GPU kernel vs the g++ build of the same source
+    (tests/hostsim, itself pinned to the oracle by tests/test_hostsim.py).  Guards against device-compiler
+    stack-slot sharing errors seen during bring-up ('toolchain hazards')."""
+    import ctypes
+    import subprocess
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "hostsim")], stdout=subprocess.DEVNULL)
+    hs = ctypes.CDLL(os.path.join(ROOT, "tests", "hostsim", "libhostsim.so"))
+    rng = random.Random(1)
+    ops = {0: (4, 2), 1: (2, 2), 2: (3, 2), 3: (6, 12), 4: (10, 12), 5: (18, 12), 6: (5, 3), 7: (2, 2), 8: (2, 2), 11: (5, 3), 12: (6, 3),
+           13: (10, 6)}
+    for op, (ni, no) in ops.items():
+        n = 64
+        data = b"".join(be(rng.randrange(Q)) for _ in range(ni * n))
+        got = E.layer_op_batch(op, data, ni, no)
+        for i in range(n):
+            o = ctypes.create_string_buffer(32 * no)
+            hs.hs_layer_op(op, data[32 * ni * i:32 * ni * (i + 1)], ni, o, no)
+            assert o.raw == got[32 * no * i:32 * no * (i + 1)], (op, i)
+    g1, g2 = O.derive_pk_g1(be(12345))[1], O.derive_pk_g2(be(6789))[1]
+    assert E.layer_op_batch(200, g1 + g2, 6, 12) == O.miller_product(g1, g2, 1)[1]
