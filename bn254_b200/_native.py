@@ -4,7 +4,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libbn254_b200.so")
+LIB_PATH = os.environ.get("BN254_B200_LIB") or os.path.join(HERE, "libbn254_b200.so")  # override: tuning builds only
 
 # every symbol include/bn254_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [

@@ -23,6 +23,10 @@ using namespace bn;
 
 #define BN_BLOCK 128
 #define BN_PROD_BLOCK 64
+// minimum resident blocks per SM requested from ptxas for the two pairing kernels (caps registers per thread)
+#ifndef BN_MINB
+#define BN_MINB 1
+#endif
 
 // ------------------------------------------------------------------------------------------------ kernels
 __global__ void k_init_lines(line_t* out) {
@@ -77,7 +81,7 @@ __global__ void __launch_bounds__(BN_BLOCK) k_sign(const g1aff* __restrict__ H, 
 }
 
 // H == NULL: the first G1 argument is the generator (check_public_keys, /root/reference/src/ecdsa.rs:78-93)
-__global__ void __launch_bounds__(BN_BLOCK) k_verify_miller(const g1aff* __restrict__ H, const uint8_t* __restrict__ sigs,
+__global__ void __launch_bounds__(BN_BLOCK, BN_MINB) k_verify_miller(const g1aff* __restrict__ H, const uint8_t* __restrict__ sigs,
                                                             const uint8_t* __restrict__ pks, size_t n, fq12* __restrict__ F,
                                                             uint8_t* __restrict__ status, const line_t* __restrict__ lines) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -96,7 +100,7 @@ __global__ void __launch_bounds__(BN_BLOCK) k_verify_miller(const g1aff* __restr
   if (!st) F[i] = f;
 }
 
-__global__ void __launch_bounds__(BN_BLOCK) k_final_exp_check(const fq12* __restrict__ F, size_t n, uint8_t* __restrict__ status) {
+__global__ void __launch_bounds__(BN_BLOCK, BN_MINB) k_final_exp_check(const fq12* __restrict__ F, size_t n, uint8_t* __restrict__ status) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   if (status[i]) return;

@@ -353,7 +353,16 @@ BN_FN fq fq_mul_ptx(const fq& a, const fq& b) {
 #endif
 
 #if defined(__CUDA_ARCH__) && !defined(BN254_PORTABLE_MUL)
+#if !defined(BN254_INLINE_MUL)
+// One out-of-line copy of the product for the whole kernel: operands and result travel in registers (by-value
+// structs use the register ABI, no stack traffic), and the pairing kernels' instruction footprint drops from
+// ~200 KB to a size the instruction cache holds -- with the product inlined at every use, two resident blocks
+// per SM spent more issue slots waiting for instruction fetch than on anything else (profiles/r01_*).
+__device__ __noinline__ fq fq_mul_call(fq a, fq b) { return fq_mul_ptx(a, b); }
+BN_FN fq fq_mul(const fq& a, const fq& b) { return fq_mul_call(a, b); }
+#else
 BN_FN fq fq_mul(const fq& a, const fq& b) { return fq_mul_ptx(a, b); }
+#endif
 #else
 BN_FN fq fq_mul(const fq& a, const fq& b) { return fq_mul_portable(a, b); }
 #endif

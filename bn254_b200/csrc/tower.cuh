@@ -38,35 +38,39 @@ BN_FN fq2 fq2_one() {
   r.c1 = fq_zero();
   return r;
 }
-BN_FN fq2 fq2_add(const fq2& a, const fq2& b) {
+// Fq2 additions are out-of-line on the device (by-value operands travel in registers): the tower and the curve
+// steps use hundreds of them, and inlining every one made the pairing kernels larger than the instruction cache.
+#if defined(__CUDA_ARCH__) && !defined(BN254_INLINE_ADD)
+#define BN_FQ2_LEAF __device__ __noinline__
+#else
+#define BN_FQ2_LEAF BN_FN
+#endif
+BN_FQ2_LEAF fq2 fq2_add_v(fq2 a, fq2 b) {
   fq2 r;
   r.c0 = fq_add(a.c0, b.c0);
   r.c1 = fq_add(a.c1, b.c1);
   return r;
 }
-BN_FN fq2 fq2_sub(const fq2& a, const fq2& b) {
+BN_FQ2_LEAF fq2 fq2_sub_v(fq2 a, fq2 b) {
   fq2 r;
   r.c0 = fq_sub(a.c0, b.c0);
   r.c1 = fq_sub(a.c1, b.c1);
   return r;
 }
-BN_FN fq2 fq2_dbl(const fq2& a) { return fq2_add(a, a); }
-BN_FN fq2 fq2_neg(const fq2& a) {
+BN_FQ2_LEAF fq2 fq2_dbl_v(fq2 a) {
+  fq2 r;
+  r.c0 = fq_add(a.c0, a.c0);
+  r.c1 = fq_add(a.c1, a.c1);
+  return r;
+}
+BN_FQ2_LEAF fq2 fq2_neg_v(fq2 a) {
   fq2 r;
   r.c0 = fq_neg(a.c0);
   r.c1 = fq_neg(a.c1);
   return r;
 }
-BN_FN fq2 fq2_conj(const fq2& a) {
-  fq2 r;
-  r.c0 = a.c0;
-  r.c1 = fq_neg(a.c1);
-  return r;
-}
-BN_FN bool fq2_is_zero(const fq2& a) { return fq_is_zero(a.c0) && fq_is_zero(a.c1); }
-BN_FN bool fq2_eq(const fq2& a, const fq2& b) { return fq_eq(a.c0, b.c0) && fq_eq(a.c1, b.c1); }
 // multiply by xi = 9 + i : (9 a0 - a1) + (9 a1 + a0) i
-BN_FN fq2 fq2_mul_xi(const fq2& a) {
+BN_FQ2_LEAF fq2 fq2_mul_xi_v(fq2 a) {
   fq t0 = fq_dbl(a.c0);
   t0 = fq_dbl(t0);
   t0 = fq_dbl(t0);
@@ -80,6 +84,19 @@ BN_FN fq2 fq2_mul_xi(const fq2& a) {
   r.c1 = fq_add(t1, a.c0);
   return r;
 }
+BN_FN fq2 fq2_add(const fq2& a, const fq2& b) { return fq2_add_v(a, b); }
+BN_FN fq2 fq2_sub(const fq2& a, const fq2& b) { return fq2_sub_v(a, b); }
+BN_FN fq2 fq2_dbl(const fq2& a) { return fq2_dbl_v(a); }
+BN_FN fq2 fq2_neg(const fq2& a) { return fq2_neg_v(a); }
+BN_FN fq2 fq2_mul_xi(const fq2& a) { return fq2_mul_xi_v(a); }
+BN_FN fq2 fq2_conj(const fq2& a) {
+  fq2 r;
+  r.c0 = a.c0;
+  r.c1 = fq_neg(a.c1);
+  return r;
+}
+BN_FN bool fq2_is_zero(const fq2& a) { return fq_is_zero(a.c0) && fq_is_zero(a.c1); }
+BN_FN bool fq2_eq(const fq2& a, const fq2& b) { return fq_eq(a.c0, b.c0) && fq_eq(a.c1, b.c1); }
 
 // Karatsuba: 3 Fq products
 BN_NOINLINE void fq2_mul(fq2* r, const fq2* a, const fq2* b) {
