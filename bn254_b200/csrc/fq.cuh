@@ -367,6 +367,13 @@ BN_FN fq fq_mul(const fq& a, const fq& b) { return fq_mul_ptx(a, b); }
 BN_FN fq fq_mul(const fq& a, const fq& b) { return fq_mul_portable(a, b); }
 #endif
 BN_FN fq fq_sqr(const fq& a) { return fq_mul(a, a); }
+// inlined product for the few routines that issue several independent products back to back (Fq2 product /
+// square / scaling): ptxas interleaves their carry chains, which hides the chains' latency
+#if defined(__CUDA_ARCH__) && !defined(BN254_PORTABLE_MUL)
+BN_FN fq fq_mul_inl(const fq& a, const fq& b) { return fq_mul_ptx(a, b); }
+#else
+BN_FN fq fq_mul_inl(const fq& a, const fq& b) { return fq_mul_portable(a, b); }
+#endif
 
 // out-of-line copies: used where code size matters more than the call
 BN_NOINLINE void fq_mul_ni(fq* r, const fq* a, const fq* b) { *r = fq_mul(*a, *b); }
