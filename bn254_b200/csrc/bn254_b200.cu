@@ -18,6 +18,7 @@
 
 #include "../../include/bn254_b200.h"
 #include "items.cuh"
+#include "coop_lines.cuh"
 
 using namespace bn;
 
@@ -231,6 +232,56 @@ __global__ void __launch_bounds__(BN_BLOCK) k_item_op(const uint8_t* __restrict_
   if (status) status[i] = (uint8_t)st;
 }
 
+// ---- cooperative pairing path (coop.cuh): per-item line sets, then six warps per 32 items run the table-driven program
+// H == NULL: the first G1 argument is the generator (check_public_keys)
+__global__ void __launch_bounds__(BN_BLOCK) k_verify_lines(const g1aff* __restrict__ H, const uint8_t* __restrict__ sigs,
+                                                           const uint8_t* __restrict__ pks, size_t n, u4* __restrict__ lines, size_t n_pad,
+                                                           uint8_t* __restrict__ status, const line_t* __restrict__ table) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (H && status[i]) return;  // hash error propagates; the item's line sets stay unwritten and its verdict is never stored
+  g1aff h;
+  if (H) {
+    h = H[i];
+  } else {
+    h.x = fq_from_limbs(K_G1_GEN_X);
+    h.y = fq_from_limbs(K_G1_GEN_Y);
+  }
+  status[i] = (uint8_t)item_verify_lines(lines, n_pad, i, &h, sigs + 64 * i, pks + 128 * i, table);
+}
+
+#ifndef BN_COOP_MINB
+#define BN_COOP_MINB 3
+#endif
+// which: 0 verify (Miller of 2 line streams + final exponentiation + verdict), 1 / 2 Miller of 1 / 2 streams -> fio,
+// 3 final exponentiation of fio (+ verdict)
+__global__ void __launch_bounds__(COOP_THREADS, BN_COOP_MINB) k_coop_run(int which, size_t n, size_t n_pad, const u4* __restrict__ lines,
+                                                                         u4* __restrict__ gslots, u4* __restrict__ fio,
+                                                                         uint8_t* __restrict__ status) {
+  extern __shared__ u4 coop_sm[];
+  coop_ctx c;
+  c.sm = coop_sm;
+  c.k = threadIdx.x >> 5;
+  c.lane = threadIdx.x & 31;
+  c.item = (size_t)blockIdx.x * COOP_LANES + c.lane;
+  c.active = c.item < n;
+  c.n_pad = n_pad;
+  c.lines = lines;
+  c.gslots = gslots;
+  c.fio = fio;
+  c.status = status;
+  const uint32_t* prog = which == 0 ? K_COOP_PROG_VERIFY : which == 1 ? K_COOP_PROG_MILLER1 : which == 2 ? K_COOP_PROG_MILLER2 : K_COOP_PROG_FINALEXP;
+#pragma unroll 1
+  for (int pc = 0;; pc++) {
+    const uint32_t ins = prog[pc];
+    if ((ins & 0xff) == COP_END) break;
+    fq2 t = coop_phase_a(c, ins);
+    __syncthreads();
+    coop_phase_b(c, ins, t);
+    __syncthreads();
+  }
+}
+
 // ---- point aggregation: strided mixed additions per thread, then a shared-memory tree per block
 template <class F> struct pt_io;
 template <> struct pt_io<fq> {
@@ -392,6 +443,7 @@ struct bn254_ctx {
   cudaStream_t stream = nullptr;
   line_t* d_lines = nullptr;
   uint64_t launches = 0;
+  int pairing_mode = 0;  // 0: cooperative six-warp machine (coop.cuh), 1: one thread per item (pairing.cuh)
   std::string err;
   // optional per-phase timing of the verify pipeline (bn254_set_profiling): events recorded on `stream`
   bool prof = false;
@@ -462,6 +514,8 @@ int bn254_ctx_create(int device, bn254_ctx** out) {
   ctx->launches++;
   if ((e = cudaGetLastError()) != cudaSuccess) return fail("k_init_lines launch", e);
   if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return fail("k_init_lines", e);
+  if ((e = cudaFuncSetAttribute(k_coop_run, cudaFuncAttributeMaxDynamicSharedMemorySize, COOP_SMEM_BYTES)) != cudaSuccess)
+    return fail("cudaFuncSetAttribute(k_coop_run)", e);
   *out = ctx;
   return 0;
 }
@@ -598,10 +652,15 @@ int bn254_sign_batch(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, const 
 // msgs == NULL: check_public_keys form (first G1 argument = generator, no hashing)
 static int verify_dev_impl(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, const uint8_t* sigs, const uint8_t* pks, size_t n,
                            uint8_t* status) {
-  const size_t CHUNK = (size_t)1 << 20;
+  const bool coop = ctx->pairing_mode == 0;
+  // chunking bounds the workspace: the cooperative path stores 174 line sets (50 KB) per item
+  const size_t CHUNK = coop ? ((size_t)1 << 17) : ((size_t)1 << 20);
   size_t cap = n < CHUNK ? n : CHUNK;
+  size_t cap_pad = (cap + COOP_LANES - 1) / COOP_LANES * COOP_LANES;
   DALLOC(H, sizeof(g1aff) * cap);
-  DALLOC(F, sizeof(fq12) * cap);
+  DALLOC(F, coop ? 16 : sizeof(fq12) * cap);
+  DALLOC(LN, coop ? sizeof(u4) * 2 * COOP_LINE_FQ * 2 * K_N_LINES * cap_pad : 16);
+  DALLOC(GS, coop ? sizeof(u4) * COOP_GSLOTS * 6 * 2 * 2 * cap_pad : 16);
   for (size_t off = 0; off < n; off += CHUNK) {
     size_t m = n - off < CHUNK ? n - off : CHUNK;
     g1aff* h = nullptr;
@@ -620,11 +679,28 @@ static int verify_dev_impl(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, 
       if (rc) return rc;
     }
     CK(mark());
-    LAUNCH(k_verify_miller, grid_for(m), BN_BLOCK, h, sigs + 64 * off, pks + 128 * off, m, F.as<fq12>(), status + off, ctx->d_lines);
-    CK(mark());
-    LAUNCH(k_final_exp_check, grid_for(m), BN_BLOCK, F.as<fq12>(), m, status + off);
-    CK(mark());
+    if (coop) {
+      size_t m_pad = (m + COOP_LANES - 1) / COOP_LANES * COOP_LANES;
+      LAUNCH(k_verify_lines, grid_for(m), BN_BLOCK, h, sigs + 64 * off, pks + 128 * off, m, LN.as<u4>(), m_pad, status + off, ctx->d_lines);
+      CK(mark());
+      k_coop_run<<<(unsigned)(m_pad / COOP_LANES), COOP_THREADS, COOP_SMEM_BYTES, ctx->stream>>>(0, m, m_pad, LN.as<u4>(), GS.as<u4>(),
+                                                                                                  (u4*)nullptr, status + off);
+      ctx->launches++;
+      CK(cudaGetLastError());
+      CK(mark());
+    } else {
+      LAUNCH(k_verify_miller, grid_for(m), BN_BLOCK, h, sigs + 64 * off, pks + 128 * off, m, F.as<fq12>(), status + off, ctx->d_lines);
+      CK(mark());
+      LAUNCH(k_final_exp_check, grid_for(m), BN_BLOCK, F.as<fq12>(), m, status + off);
+      CK(mark());
+    }
   }
+  return 0;
+}
+int bn254_set_pairing_mode(bn254_ctx* ctx, int mode) {
+  ENTER();
+  ARGCHECK(mode == 0 || mode == 1);
+  ctx->pairing_mode = mode;
   return 0;
 }
 int bn254_set_profiling(bn254_ctx* ctx, int on) {

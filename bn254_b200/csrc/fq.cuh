@@ -174,6 +174,15 @@ BN_FN fq fq_sub(const fq& a, const fq& b) {
 }
 #endif
 BN_FN fq fq_dbl(const fq& a) { return fq_add(a, a); }
+// conditional subtraction: a in [0, 2^256) -> a - q if a >= q else a
+BN_FN fq fq_csub(const fq& a) {
+  fq t;
+  const uint32_t qq[8] = {BN_Q0, BN_Q1, BN_Q2, BN_Q3, BN_Q4, BN_Q5, BN_Q6, BN_Q7};
+  uint32_t bw = u256_sub(t.l, a.l, qq);
+#pragma unroll
+  for (int i = 0; i < 8; i++) t.l[i] = bw ? a.l[i] : t.l[i];
+  return t;
+}
 BN_FN fq fq_neg(const fq& a) { return fq_sub(fq_zero(), a); }
 
 // ------------------------------------------------------------------------------------------------ Montgomery product

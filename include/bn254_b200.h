@@ -63,8 +63,13 @@ uint64_t bn254_launch_count(bn254_ctx* ctx);   /* kernels launched by this conte
 
 /* measurement support: when on, the verify pipeline brackets its three kernels (hash, Miller loop, final
  * exponentiation) with CUDA events on the context's stream; bn254_phase_ms returns and clears the accumulated times */
+/* the verify pipeline's three phases: hash / Miller / final exponentiation with mode 1, hash / line sets / cooperative
+ * Miller + final exponentiation with mode 0 */
 int bn254_set_profiling(bn254_ctx* ctx, int on);
 int bn254_phase_ms(bn254_ctx* ctx, float* out3);
+/* pairing kernels used by verify / check_public_keys: 0 (default) = cooperative machine, six warps share the Fq12 value of
+ * 32 items (csrc/coop.cuh); 1 = one thread per item (csrc/pairing.cuh).  Both give identical verdicts (tests compare them). */
+int bn254_set_pairing_mode(bn254_ctx* ctx, int mode);
 
 /* hash_to_try_and_increment (/root/reference/src/hash.rs:29-63): n messages of msg_len bytes each -> G1 */
 int bn254_hash_to_g1_batch(bn254_ctx*, const uint8_t* msgs, size_t msg_len, size_t n, uint8_t* g1_out, uint8_t* status);

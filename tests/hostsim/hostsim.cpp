@@ -166,3 +166,117 @@ API int hs_layer_op(int op, const uint8_t* in, int n_in, uint8_t* out, int n_out
   for (int k = 0; k < n_out && k < 12; k++) fq_to_be(out + 32 * k, r[k]);
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------- cooperative machine
+// The six warps of a block are simulated one after the other, phase by phase, for lane 0 of one block.
+#include "../../bn254_b200/csrc/coop_lines.cuh"
+#include <vector>
+
+struct coop_sim {
+  std::vector<u4> sm, lines, gslots, fio;
+  uint8_t status = 0;
+  size_t n_pad = COOP_LANES;
+  coop_sim() : sm(COOP_SLOTS * 2 * COOP_LANES), lines((size_t)2 * K_N_LINES * COOP_LINE_FQ * 2 * COOP_LANES),
+               gslots((size_t)COOP_GSLOTS * 6 * 2 * 2 * COOP_LANES), fio((size_t)6 * 2 * 2 * COOP_LANES) {}
+  coop_ctx ctx(int k) {
+    coop_ctx c;
+    c.sm = sm.data(); c.k = k; c.lane = 0; c.active = true; c.item = 0; c.n_pad = n_pad;
+    c.lines = lines.data(); c.gslots = gslots.data(); c.fio = fio.data(); c.status = &status;
+    return c;
+  }
+  void run(const uint32_t* prog) {
+    for (int pc = 0;; pc++) {
+      uint32_t ins = prog[pc];
+      if ((ins & 0xff) == COP_END) break;
+      fq2 t[COOP_WARPS];
+      for (int k = 0; k < COOP_WARPS; k++) t[k] = coop_phase_a(ctx(k), ins);
+      for (int k = 0; k < COOP_WARPS; k++) coop_phase_b(ctx(k), ins, t[k]);
+    }
+  }
+  // tower order c0.c0, c0.c1, c0.c2, c1.c0, c1.c1, c1.c2 <- a0, a2, a4, a1, a3, a5
+  void get_fio(fq12* f) {
+    static const int pos[6] = {0, 2, 4, 1, 3, 5};
+    fq2* c = &f->c0.c0;
+    for (int t = 0; t < 6; t++) {
+      c[t].c0 = coop_gld(fio.data(), (size_t)pos[t] * 2 + 0, n_pad, 0);
+      c[t].c1 = coop_gld(fio.data(), (size_t)pos[t] * 2 + 1, n_pad, 0);
+    }
+  }
+  void set_fio(const fq12* f) {
+    static const int pos[6] = {0, 2, 4, 1, 3, 5};
+    const fq2* c = &f->c0.c0;
+    for (int t = 0; t < 6; t++) {
+      coop_gst(fio.data(), (size_t)pos[t] * 2 + 0, n_pad, 0, c[t].c0);
+      coop_gst(fio.data(), (size_t)pos[t] * 2 + 1, n_pad, 0, c[t].c1);
+    }
+  }
+};
+
+// full verify through the cooperative program; h_is_gen: check_public_keys form
+API int hs_coop_verify(const uint8_t* msg, size_t len, const uint8_t* sig, const uint8_t* pk, int h_is_gen) {
+  ensure_init();
+  g1aff h;
+  if (h_is_gen) {
+    h.x = fq_from_limbs(K_G1_GEN_X); h.y = fq_from_limbs(K_G1_GEN_Y);
+  } else {
+    int st = hash_to_g1(&h.x, &h.y, msg, len, nullptr);
+    if (st) return st;
+  }
+  coop_sim S;
+  int st = item_verify_lines(S.lines.data(), S.n_pad, 0, &h, sig, pk, g_lines);
+  if (st) return st;
+  S.run(K_COOP_PROG_VERIFY);
+  return S.status;
+}
+// Miller product of the verify pairs (tower order, big-endian) through the cooperative program
+API int hs_coop_verify_miller(const uint8_t* msg, size_t len, const uint8_t* sig, const uint8_t* pk, uint8_t* f_out) {
+  ensure_init();
+  g1aff h;
+  int st = hash_to_g1(&h.x, &h.y, msg, len, nullptr);
+  if (st) return st;
+  coop_sim S;
+  st = item_verify_lines(S.lines.data(), S.n_pad, 0, &h, sig, pk, g_lines);
+  if (st) return st;
+  S.run(K_COOP_PROG_MILLER2);
+  fq12 f;
+  S.get_fio(&f);
+  fq12_to_be(f_out, &f);
+  return 0;
+}
+API int hs_coop_final_exp(const uint8_t* f_in, uint8_t* gt_out) {
+  fq12 f, gt;
+  if (!fq12_from_be(&f, f_in)) return ST_NOT_MEMBER;
+  coop_sim S;
+  S.set_fio(&f);
+  S.run(K_COOP_PROG_FINALEXP);
+  S.get_fio(&gt);
+  fq12_to_be(gt_out, &gt);
+  return S.status;
+}
+// one plan applied to given P (and S) values: op 0 MUL (P <- S*P), 1 SQR, 3 CYCLO ; values in tower order
+API int hs_coop_plan(int plan, const uint8_t* p_in, const uint8_t* s_in, uint8_t* out) {
+  fq12 p, s, r;
+  if (!fq12_from_be(&p, p_in)) return ST_NOT_MEMBER;
+  if (s_in && !fq12_from_be(&s, s_in)) return ST_NOT_MEMBER;
+  coop_sim S;
+  S.set_fio(&p);
+  uint32_t prog[8];
+  int n = 0;
+  if (s_in) {
+    S.set_fio(&s);
+    prog[n++] = COP_LOADF;
+    prog[n++] = COP_STORE | (0 << 8);
+    S.run((prog[n] = COP_END, prog));
+    n = 0;
+    S.set_fio(&p);
+  }
+  prog[n++] = COP_LOADF;
+  if (s_in) prog[n++] = COP_LOADS | (0 << 8);
+  prog[n++] = COP_DOT | (plan << 8);
+  prog[n++] = COP_STOREF;
+  prog[n++] = COP_END;
+  S.run(prog);
+  S.get_fio(&r);
+  fq12_to_be(out, &r);
+  return 0;
+}

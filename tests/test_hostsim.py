@@ -214,3 +214,59 @@ def test_codecs(hs):
         x += 1
     raw = be(x) + be(0) + be(y[0]) + be(y[1])
     assert hs.hs_g2_validate(raw, 128) == O.INVALID_GROUP_POINT == O.g2_validate_uncompressed(raw)
+
+
+# ---------------------------------------------------------------------------------------------- cooperative machine
+def test_coop_plans_match_tower(hs):
+    """One plan of the six-warp machine == the tower formula of the oracle (product, square, cyclotomic square)."""
+    rng = random.Random(11)
+    for _ in range(6):
+        a, b = rand_fq12(rng), rand_fq12(rng)
+        out = buf(384)
+        assert hs.hs_coop_plan(0, a, b, out) == 0 and out.raw == O.fq12_op(0, a, b)[1]   # P <- S * P
+        assert hs.hs_coop_plan(1, a, None, out) == 0 and out.raw == O.fq12_op(1, a)[1]   # P <- P^2
+    # cyclotomic squaring is only defined on the cyclotomic subgroup: use final-exponentiation outputs
+    for _ in range(3):
+        g = O.final_exp(rand_fq12(rng))[1]
+        out = buf(384)
+        assert hs.hs_coop_plan(3, g, None, out) == 0 and out.raw == O.fq12_op(3, g)[1] == O.fq12_op(1, g)[1]
+    edge = be(Q - 1) * 12
+    out = buf(384)
+    assert hs.hs_coop_plan(0, edge, edge, out) == 0 and out.raw == O.fq12_op(0, edge, edge)[1]
+    assert hs.hs_coop_plan(1, edge, None, out) == 0 and out.raw == O.fq12_op(1, edge)[1]
+
+
+def test_coop_final_exp(hs):
+    rng = random.Random(12)
+    for _ in range(3):
+        f = rand_fq12(rng)
+        gt = buf(384)
+        st = hs.hs_coop_final_exp(f, gt)
+        assert gt.raw == O.final_exp(f)[1]
+        assert st == O.VERIFICATION_FAILED  # a random value does not map to one
+
+
+def test_coop_verify_matches_oracle(hs):
+    rng = random.Random(13)
+    neg_g2 = O.g2_neg(O.derive_pk_g2(be(1))[1])[1]
+    for t in range(4):
+        sk = be(rng.randrange(1, R))
+        msg = rng.randbytes(32)
+        sig = O.sign(msg, sk)[1]
+        pk = O.derive_pk_g2(sk)[1]
+        f = buf(384)
+        assert hs.hs_coop_verify_miller(msg, len(msg), sig, pk, f) == 0
+        assert f.raw == O.miller_product(O.hash_to_g1(msg)[1] + sig, pk + neg_g2, 2)[1]
+        assert hs.hs_coop_verify(msg, len(msg), sig, pk, 0) == 0
+        bad = O.g1_add(sig, G1_GEN)[1]
+        assert hs.hs_coop_verify(msg, len(msg), bad, pk, 0) == O.VERIFICATION_FAILED
+        assert hs.hs_coop_verify(msg + b"x", len(msg) + 1, sig, pk, 0) == O.VERIFICATION_FAILED
+    # infinity semantics of bn::pairing_batch (pairs holding an infinity are skipped) and decode errors
+    assert hs.hs_coop_verify(b"m", 1, bytes(64), bytes(128), 0) == 0 == O.verify(b"m", bytes(64), bytes(128))
+    assert hs.hs_coop_verify(b"m", 1, bytes(64), pk, 0) == O.VERIFICATION_FAILED
+    assert hs.hs_coop_verify(b"m", 1, sig, bytes(128), 0) == O.VERIFICATION_FAILED
+    assert hs.hs_coop_verify(b"m", 1, be(1) + be(3), pk, 0) == O.INVALID_GROUP_POINT
+    for v in G["check_public_keys_ok"]:
+        assert hs.hs_coop_verify(b"", 0, O.derive_pk_g1(H(v["sk"]))[1], O.derive_pk_g2(H(v["sk"]))[1], 1) == 0
+    for v in G["check_public_keys_fail"]:
+        assert hs.hs_coop_verify(b"", 0, O.derive_pk_g1(H(v["sk_g1"]))[1], O.derive_pk_g2(H(v["sk_g2"]))[1], 1) == O.VERIFICATION_FAILED
