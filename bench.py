@@ -9,10 +9,11 @@ A step = one pass of ECDSA::verify over a batch of 2^20 independent (32-byte msg
               engine's stream, max over ranks)
   e2e         the same metric through the public host-buffer entry point (bn254_verify_batch via
               bn254_b200.engine.verify_batch): pinned host inputs, H2D + kernels + D2H of the verdicts timed
-  roofline    INT32 multiply-pipe roofline of the dominant phase (Miller loop + final exponentiation):
-              achieved = algorithmic IMAD32 (264 per Fq product) per second, peak = the IMAD issue
-              rate measured live by tools/microbench.bin on this GPU (the path is integer-issue bound: a verify
-              reads 224 B and does ~5.8 M IMAD32-equivalents, so neither HBM nor tensor peak applies)
+  roofline    INT32 multiply-pipe roofline of the dominant kernel (k_coop_run: Miller accumulation + final
+              exponentiation): achieved = algorithmic IMAD32 (264 per Fq product) per second over the
+              kernel's CUDA-event time, peak = the IMAD issue rate measured live by tools/microbench.bin on this GPU
+              (the path is integer-issue bound: a verify reads 224 B and does ~5.8 M IMAD32-equivalents, so neither
+              HBM nor tensor peak applies; the HBM figures are reported beside it to show that)
   cpu_baseline  the oracle (C restatement of the dependency's algorithms) timed on the host cores, bounded sample
 `--impl reference` times the CPU path alone (the Rust crate cannot be built here: no cargo/rustc; oracle/ port).
 """
@@ -29,9 +30,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-M_VERIFY = 21885        # Fq-mul equivalents per verify
-M_PAIRING_PART = 21111  # Miller (2-pair, shared squarings) + final exponentiation share of a verify
-IMAD_PER_M = 264
+# Fq-product equivalents per verify, fixed numerators of SURVEY.md 8(d) (21 885 in total), split by the kernel that
+# does the work in the cooperative pipeline:
+M_HASH = 774            # k_hash_to_g1: try-and-increment, 2.116 expected tries
+M_LINES = 3083          # k_verify_lines: G2 doubling / addition steps (64 x 28 + 23 x 41) + scaling of the -G2 lines (87 x 4)
+M_COOP = 18028          # k_coop_run: f^2 chain 2 304 + 2 x 87 sparse products x 39 + final exponentiation 8 938
+M_VERIFY = M_HASH + M_LINES + M_COOP
+IMAD_PER_M = 264        # IMAD32 issue slots per Fq product (an IMAD.WIDE.U32.X costs two: profiles/r01_tuning_log.md)
 METRIC = "bn254_verifies_per_sec"
 UNIT = "verifies/s"
 
@@ -101,7 +106,7 @@ def run_reference(args):
     import oracle_lib as O
     import synth
     threads = os.cpu_count() or 1
-    n = args.cpu_sample or max(256, 128 * threads)
+    n = args.cpu_sample or max(256, 4096 * threads)  # ~10 s of CPU work per step at ~0.5 k verifies/s/thread
     msgs, sks = synth.messages(n, 32, seed=1), synth.secret_keys(n, seed=2)
     sigs, st = O.sign_batch(msgs, 32, sks, n, threads)
     pks = O.derive_pk_g2_batch(sks, n, threads)
@@ -234,17 +239,34 @@ def run_engine(args):
 
     cal = imad_peak()
     peak = cal.get("imad_lo", {}).get("gops") if isinstance(cal, dict) else None
-    pairing_ms = phase[1] + phase[2]
-    achieved = (n * M_PAIRING_PART * IMAD_PER_M / (pairing_ms * 1e-3) / 1e9) if pairing_ms > 0 else None
+    # phase[0] hash, phase[1] line sets, phase[2] cooperative Miller + final exponentiation (one profiled step)
+    coop_ms = phase[2]
+    achieved = (n * M_COOP * IMAD_PER_M / (coop_ms * 1e-3) / 1e9) if coop_ms > 0 else None
+    step_ms = ms_total / args.steps
+    traffic, hbm = None, None
+    try:  # DRAM bytes of one k_coop_run launch from the committed ncu capture (not measured live)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        traffic = tj["k_coop_run"]["dram_bytes_per_launch"]
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        launch_ms = coop_ms / max(1, (n + (1 << 17) - 1) >> 17)
+        items = min(n, 1 << 17)
+        hbm = {"achieved_gbs": traffic * items / tj["k_coop_run"]["items_per_launch"] / (launch_ms * 1e-3) / 1e9,
+               "peak_gbs": peaks.get("hbm_gbs", 6650.0), "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"}
+        hbm["frac"] = hbm["achieved_gbs"] / hbm["peak_gbs"]
+    except Exception:
+        pass
     roof = {
-        "bound": "int32_imad", "kernel": "k_verify_miller + k_final_exp_check", "achieved": achieved, "peak": peak, "unit": "GIMAD32/s",
-        "frac": (achieved / peak if achieved and peak else None), "traffic": None,
+        "bound": "int32_imad", "kernel": "k_coop_run", "achieved": achieved, "peak": peak, "unit": "GIMAD32/s",
+        "frac": (achieved / peak if achieved and peak else None), "traffic": traffic,
         "peak_source": "tools/microbench.bin mad.lo.u32 chain measured in this run (MEASURED_PEAKS.json has no int32 figure)",
-        "phase_ms": {"hash_to_g1": phase[0], "miller": phase[1], "final_exp": phase[2]},
-        "calibration": cal,
+        "algorithmic_per_unit": {"k_hash_to_g1": M_HASH * IMAD_PER_M, "k_verify_lines": M_LINES * IMAD_PER_M, "k_coop_run": M_COOP * IMAD_PER_M,
+                                 "unit": "IMAD32 per verify"},
+        "whole_step_frac": (n * M_VERIFY * IMAD_PER_M / (step_ms * 1e-3) / 1e9 / peak) if peak else None,
+        "phase_ms": {"hash_to_g1": phase[0], "line_sets": phase[1], "miller_and_final_exp": phase[2]},
+        "hbm": hbm, "calibration": cal,
     }
     threads = os.cpu_count() or 1
-    n_cpu = args.cpu_sample or max(256, 64 * threads)
+    n_cpu = args.cpu_sample or min(n, max(256, 5120 * threads))  # bounded sample: ~10 s of CPU work
     cpu_v, cpu_dt, cpu_st = cpu_baseline(n_cpu, msgs, sigs, pks, threads)
     assert cpu_st == bytes(n_cpu)
     line = {
@@ -253,7 +275,7 @@ def run_engine(args):
         "data": "synthetic",
         "config": {"workload": "batch verify 2^20 independent (32-byte msg, sig, pk) triples per GPU (BASELINE configs[1])",
                    "triples_per_gpu": n, "msg_len": 32, "l2": "inputs+workspace (%.0f MB) larger than L2" % ((224 + 448) * n / 1e6),
-                   "pairings_per_sec": value * 2},
+                   "pairings_per_sec": value * 2, "pairing_kernels": "cooperative (six warps per 32 items), chunks of 2^17"},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 224 * n, "d2h_bytes_per_step": n, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches, "clocks": sampler.result(), "roofline": roof,
         "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": threads, "kind": "port",

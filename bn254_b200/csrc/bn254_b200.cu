@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(BN_BLOCK) k_verify_lines(const g1aff* __restri
 }
 
 #ifndef BN_COOP_MINB
-#define BN_COOP_MINB 3
+#define BN_COOP_MINB 4
 #endif
 // which: 0 verify (Miller of 2 line streams + final exponentiation + verdict), 1 / 2 Miller of 1 / 2 streams -> fio,
 // 3 final exponentiation of fio (+ verdict)

@@ -236,14 +236,16 @@ def plan_sqr():
     return rows
 
 
-def plan_sparse():
-    # P * (l0 + l3 w^3 + l4 w^4), line coefficients in S records 0, 3, 4
+def plan_sparse(buf):
+    # P * (l0 + l3 w^3 + l4 w^4); the line coefficients sit in S triples (0, 3, 4) [buffer 0] or (1, 2, 5) [buffer 1]:
+    # consecutive line sets alternate between the two so that the next one can be fetched while this one is read
+    t0, t3, t4 = ((0, 3, 4), (1, 2, 5))[buf]
     rows = []
     for k in range(6):
-        es = [(P_PLAIN(k), S_T(0))]
-        for d in (3, 4):
+        es = [(P_PLAIN(k), S_T(t0))]
+        for d, t in ((3, t3), (4, t4)):
             i = (k - d) % 6
-            es.append((P_PLAIN(i) if i + d == k else P_XI(i), S_T(d)))
+            es.append((P_PLAIN(i) if i + d == k else P_XI(i), S_T(t)))
         rows.append(row(es, dest=k))
     return rows
 
@@ -288,7 +290,7 @@ def plan_inv_c():
     return rows
 
 
-PLANS = [("MUL", plan_mul), ("SQR", plan_sqr), ("SPARSE", plan_sparse), ("CYCLO", plan_cyclo), ("INV_A", plan_inv_a), ("INV_B", plan_inv_b),
+PLANS = [("MUL", plan_mul), ("SQR", plan_sqr), ("SPARSE_A", lambda: plan_sparse(0)), ("SPARSE_B", lambda: plan_sparse(1)), ("CYCLO", plan_cyclo), ("INV_A", plan_inv_a), ("INV_B", plan_inv_b),
          ("INV_C", plan_inv_c)]
 
 # ------------------------------------------------------------------------------------------------ programs
@@ -308,28 +310,50 @@ ATE = [1, 0, 1, 0, 0, 0, -1, 0, -1, 0, 0, 0, -1, 0, 1, 0, -1, 0, 0, -1, 0, 0, 0,
 U = 4965661367192848881
 
 
+def dot(plan, prefetch=None, buf=0):
+    """DOT instruction; prefetch = line set to fetch into S buffer `buf` while the dot product runs"""
+    a2 = 0 if prefetch is None else ((prefetch + 1) | (buf << 8))
+    return ins("DOT", PLAN_ID[plan], a2)
+
+
 def prog_miller(pairs):
     """f = product over `pairs` line streams: per step the lines of pair 0, pair 1, ... are consumed in order; line sets
-    are numbered in exactly this order by the line kernel."""
-    p = [ins("ONE")]
+    are numbered in exactly this order by the line kernel.  Line set m goes to S buffer m & 1; every arithmetic
+    instruction fetches the next line set into the other buffer."""
+    ops = []  # ("SQR",) or ("SPARSE", m)
     idx = 0
 
     def lines():
         nonlocal idx
         for _ in range(pairs):
-            p.append(ins("LINE", 0, idx))
-            p.append(ins("DOT", PLAN_ID["SPARSE"]))
+            ops.append(("SPARSE", idx))
             idx += 1
 
     for k in range(64):
         if k > 0:
-            p.append(ins("DOT", PLAN_ID["SQR"]))
+            ops.append(("SQR",))
         lines()
         if ATE[k]:
             lines()
     lines()
     lines()
-    assert idx == 87 * pairs
+    total = 87 * pairs
+    assert idx == total
+    p = [ins("ONE"), ins("LINE", 0, 0)]
+    fetched = 0  # highest line set already requested
+    for o in ops:
+        nxt = fetched + 1 if fetched + 1 < total else None
+        if o[0] == "SQR":
+            # the set needed next is already in place (requested by the instruction before); fetch nothing new
+            p.append(dot("SQR"))
+        else:
+            m = o[1]
+            assert m <= fetched
+            pf = None
+            if m == fetched and nxt is not None:
+                pf = nxt
+                fetched = nxt
+            p.append(dot("SPARSE_A" if m % 2 == 0 else "SPARSE_B", pf, (pf or 0) & 1))
     return p
 
 
@@ -411,6 +435,51 @@ def prog_final_exp():
     return p
 
 
+def plan_info():
+    """per plan: set of P records whose xi variant is read, and whether the plan overwrites P"""
+    info = {}
+    for pid, (name, fn) in enumerate(PLANS):
+        rows_ = fn()
+        xi = set()
+        for r in rows_:
+            for e in r["e"]:
+                for slot in (e & 0xff, (e >> 8) & 0xff):
+                    if slot < 36 and slot % 6 == 3:
+                        xi.add(slot // 6)
+        writes_p = any(r["dest"] < 6 for r in rows_)
+        info[pid] = (xi, writes_p)
+    return info
+
+
+def add_xi_skip(prog):
+    """DOT instructions that write P get, in bits 9..14 of arg2, the records whose xi variant nobody reads before P is
+    rewritten -- the machine then skips computing them (ten modular additions per record)."""
+    info = plan_info()
+    rewrites = {OPC["LOADP"], OPC["LOADF"], OPC["ONE"]}
+    out = list(prog)
+    for t, w in enumerate(prog):
+        if (w & 0xff) != OPC["DOT"] or not info[(w >> 8) & 0xff][1]:
+            continue
+        need = set()
+        for u in prog[t + 1:]:
+            op = u & 0xff
+            if op == OPC["DOT"]:
+                xi, wp = info[(u >> 8) & 0xff]
+                need |= xi
+                if wp:
+                    break
+            elif op in rewrites:
+                break
+            elif op == OPC["FROBP"]:
+                break  # rewrites every record (with all variants) from the plain parts; CONJP only rewrites the odd ones
+        skip = 0
+        for k in range(6):
+            if k not in need:
+                skip |= 1 << k
+        out[t] = w | (skip << (16 + 9))
+    return out
+
+
 def f2_mul(a, b):
     return ((a[0] * b[0] - a[1] * b[1]) % Q, (a[0] * b[1] + a[1] * b[0]) % Q)
 
@@ -446,10 +515,11 @@ def gen_tables():
             o.append("    {0x%05x, %s}," % (w0, ", ".join(es)))
         o.append("  },")
     o.append("};")
-    for name, prog in (("VERIFY", prog_miller(2) + prog_final_exp() + [ins("CHECK"), ins("END")]),
+    for name, prog0 in (("VERIFY", prog_miller(2) + prog_final_exp() + [ins("CHECK"), ins("END")]),
                        ("MILLER1", prog_miller(1) + [ins("STOREF"), ins("END")]),
                        ("MILLER2", prog_miller(2) + [ins("STOREF"), ins("END")]),
                        ("FINALEXP", [ins("LOADF")] + prog_final_exp() + [ins("STOREF"), ins("CHECK"), ins("END")])):
+        prog = add_xi_skip(prog0)
         o.append("#define K_COOP_PROG_%s_LEN %d" % (name, len(prog)))
         o.append("BN_CONST uint32_t K_COOP_PROG_%s[%d] = {" % (name, len(prog)))
         for i in range(0, len(prog), 12):

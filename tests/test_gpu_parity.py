@@ -427,3 +427,37 @@ def test_layer_hooks_match_host_simulation(E):
             assert o.raw == got[32 * no * i:32 * no * (i + 1)], (op, i)
     g1, g2 = O.derive_pk_g1(be(12345))[1], O.derive_pk_g2(be(6789))[1]
     assert E.layer_op_batch(200, g1 + g2, 6, 12) == O.miller_product(g1, g2, 1)[1]
+
+
+def test_pairing_modes_agree_on_ragged_batches(E):
+    """The cooperative machine (mode 0, csrc/coop.cuh) and the one-thread-per-item kernels (mode 1, csrc/pairing.cuh) are two
+    independent implementations of bn::pairing_batch: identical verdicts on batches whose size is not a multiple of the
+    32-item group, including a single item, with invalid items in every position class."""
+    from bn254_b200._native import I
+    ctx = E.context(0)
+    n = 1000
+    msgs, sks, sigs, pks = _signed_set(E, n, seed=77)
+    sigs, pks = bytearray(sigs), bytearray(pks)
+    for i in (0, 31, 32, 33, 63, 500, 991, 999):  # group boundaries and the ragged tail
+        sigs[64 * i:64 * i + 64] = O.g1_neg(bytes(sigs[64 * i:64 * i + 64]))[1]
+    sigs[64 * 7:64 * 8] = bytes(64)
+    pks[128 * 7:128 * 8] = bytes(128)      # both infinite: accepted
+    sigs[64 * 9 + 63] ^= 1                 # off curve
+    sigs, pks = bytes(sigs), bytes(pks)
+    want = O.verify_batch(msgs, 32, sigs, pks, n, NTHREADS)
+    for size in (1000, 1, 33, 95):
+        got = {}
+        for mode in (0, 1):
+            ctx.call("bn254_set_pairing_mode", I(mode))
+            got[mode] = E.verify_batch(msgs[:32 * size], 32, sigs[:64 * size], pks[:128 * size], ctx=ctx)
+        ctx.call("bn254_set_pairing_mode", I(0))
+        assert got[0] == got[1] == want[:size], size
+    # check_public_keys goes through the same two paths (generator instead of H(m))
+    pk1 = E.derive_pk_g1_batch(sks[:32 * 40], ctx=ctx)
+    pk2 = bytearray(pks[:128 * 40])
+    pk2[128 * 3:128 * 4] = pks[128 * 4:128 * 5]
+    for mode in (0, 1):
+        ctx.call("bn254_set_pairing_mode", I(mode))
+        st = E.check_public_keys_batch(bytes(pk2), pk1, ctx=ctx)
+        assert st[3] == O.VERIFICATION_FAILED and st[7] != 0 and sum(1 for s in st if s == 0) == 38, (mode, st)
+    ctx.call("bn254_set_pairing_mode", I(0))

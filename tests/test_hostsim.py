@@ -229,7 +229,7 @@ def test_coop_plans_match_tower(hs):
     for _ in range(3):
         g = O.final_exp(rand_fq12(rng))[1]
         out = buf(384)
-        assert hs.hs_coop_plan(3, g, None, out) == 0 and out.raw == O.fq12_op(3, g)[1] == O.fq12_op(1, g)[1]
+        assert hs.hs_coop_plan(4, g, None, out) == 0 and out.raw == O.fq12_op(3, g)[1] == O.fq12_op(1, g)[1]
     edge = be(Q - 1) * 12
     out = buf(384)
     assert hs.hs_coop_plan(0, edge, edge, out) == 0 and out.raw == O.fq12_op(0, edge, edge)[1]
