@@ -57,6 +57,54 @@ __global__ void __launch_bounds__(BN_BLOCK) k_hash_to_g1(const uint8_t* __restri
   if (tries) tries[i] = (uint8_t)ctr;
 }
 
+// ---- compacting hash: round r tries counter r for every item still without a point; items that fail are appended to the
+// next round's list (warp-aggregated), so a warp never idles behind its slowest lane (the accept probability is 0.47 per
+// try: the per-thread loop above spends ~3x the useful tries at warp granularity).  Messages of at most 54 bytes only.
+__global__ void __launch_bounds__(BN_BLOCK) k_hash_round(const uint8_t* __restrict__ msgs, uint32_t msg_len, uint32_t n, uint32_t ctr,
+                                                         const uint32_t* __restrict__ list_in, const uint32_t* __restrict__ count_in,
+                                                         uint32_t* __restrict__ list_out, uint32_t* __restrict__ count_out,
+                                                         g1aff* __restrict__ H, uint8_t* __restrict__ status) {
+  const uint32_t total = list_in ? *count_in : n;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const uint32_t i = list_in ? list_in[t] : t;
+    g1aff h;
+    const bool ok = hash_try_1blk(&h.x, &h.y, msgs + (size_t)i * msg_len, msg_len, ctr);
+    if (ok) {
+      H[i] = h;
+      status[i] = ST_OK;
+    }
+    const unsigned active = __activemask();
+    const unsigned fail = __ballot_sync(active, !ok);
+    if (!ok) {
+      const unsigned lane = threadIdx.x & 31, leader = __ffs(fail) - 1;
+      uint32_t base = 0;
+      if (lane == leader) base = atomicAdd(count_out, (uint32_t)__popc(fail));
+      base = __shfl_sync(fail, base, leader);
+      list_out[base + __popc(fail & ((1u << lane) - 1))] = i;
+    }
+  }
+}
+// the few items that survive the compacting rounds finish with the per-thread loop (counters ctr0 .. 254)
+__global__ void __launch_bounds__(BN_BLOCK) k_hash_tail(const uint8_t* __restrict__ msgs, uint32_t msg_len, uint32_t ctr0,
+                                                        const uint32_t* __restrict__ list_in, const uint32_t* __restrict__ count_in,
+                                                        g1aff* __restrict__ H, uint8_t* __restrict__ status) {
+  const uint32_t total = *count_in;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const uint32_t i = list_in[t];
+    g1aff h;
+    bool ok = false;
+    for (uint32_t ctr = ctr0; ctr < 255 && !ok; ctr++) ok = hash_try_1blk(&h.x, &h.y, msgs + (size_t)i * msg_len, msg_len, ctr);
+    if (!ok) {
+      h.x = fq_zero();
+      h.y = fq_zero();
+    }
+    H[i] = h;
+    status[i] = ok ? ST_OK : ST_HASH_TO_POINT;
+  }
+}
+
 __global__ void __launch_bounds__(BN_BLOCK) k_g1aff_to_raw(const g1aff* __restrict__ H, const uint8_t* __restrict__ status, size_t n,
                                                            uint8_t* __restrict__ out) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -250,6 +298,11 @@ __global__ void __launch_bounds__(BN_BLOCK) k_verify_lines(const g1aff* __restri
   status[i] = (uint8_t)item_verify_lines(lines, n_pad, i, &h, sigs + 64 * i, pks + 128 * i, table);
 }
 
+#if defined(COOP_ABLATE_NOBAR)  // timing experiment only: results are wrong without the barriers
+#define COOP_BARRIER() __syncwarp()
+#else
+#define COOP_BARRIER() __syncthreads()
+#endif
 #ifndef BN_COOP_MINB
 #define BN_COOP_MINB 4
 #endif
@@ -276,9 +329,9 @@ __global__ void __launch_bounds__(COOP_THREADS, BN_COOP_MINB) k_coop_run(int whi
     const uint32_t ins = prog[pc];
     if ((ins & 0xff) == COP_END) break;
     fq2 t = coop_phase_a(c, ins);
-    __syncthreads();
+    COOP_BARRIER();
     coop_phase_b(c, ins, t);
-    __syncthreads();
+    COOP_BARRIER();
   }
 }
 
@@ -564,10 +617,33 @@ uint64_t bn254_launch_count(bn254_ctx* ctx) { return ctx ? ctx->launches : 0; }
   CK(name.alloc(bytes))
 
 // ---- device-pointer pipelines (asynchronous on ctx->stream)
+#define BN_HASH_ROUNDS 12
 static int hash_dev(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, const uint64_t* offsets, size_t n, g1aff* H, uint8_t* status,
                     uint8_t* tries) {
   if (n == 0) return 0;
-  LAUNCH(k_hash_to_g1, grid_for(n), BN_BLOCK, msgs, msg_len, offsets, n, H, status, tries);
+  // small batches, ragged messages, multi-block messages and callers that want the counters: one thread loops per item
+  if (offsets || tries || msg_len > 54 || n < 4096 || n > 0xffffffffu) {
+    LAUNCH(k_hash_to_g1, grid_for(n), BN_BLOCK, msgs, msg_len, offsets, n, H, status, tries);
+    return 0;
+  }
+  // compacting rounds: expected survivors of round r = n * 0.527^r; grids are sized with a margin and stride over the list
+  DALLOC(lists, sizeof(uint32_t) * 2 * n);
+  DALLOC(counts, sizeof(uint32_t) * (BN_HASH_ROUNDS + 1));
+  CK(cudaMemsetAsync(counts.p, 0, sizeof(uint32_t) * (BN_HASH_ROUNDS + 1), ctx->stream));
+  uint32_t* L[2] = {lists.as<uint32_t>(), lists.as<uint32_t>() + n};
+  uint32_t* C = counts.as<uint32_t>();
+  double expect = (double)n;
+  for (int r = 0; r < BN_HASH_ROUNDS; r++) {
+    size_t threads = r == 0 ? n : (size_t)(expect * 1.25) + 4096;
+    if (threads > n) threads = n;
+    LAUNCH(k_hash_round, grid_for(threads), BN_BLOCK, msgs, (uint32_t)msg_len, (uint32_t)n, (uint32_t)r, r == 0 ? (const uint32_t*)nullptr : L[(r - 1) & 1],
+           r == 0 ? (const uint32_t*)nullptr : C + r, L[r & 1], C + r + 1, H, status);
+    expect *= 0.5275;
+  }
+  size_t threads = (size_t)(expect * 1.25) + 4096;
+  if (threads > n) threads = n;
+  LAUNCH(k_hash_tail, grid_for(threads), BN_BLOCK, msgs, (uint32_t)msg_len, (uint32_t)BN_HASH_ROUNDS, L[(BN_HASH_ROUNDS - 1) & 1], C + BN_HASH_ROUNDS, H,
+         status);
   return 0;
 }
 

@@ -122,4 +122,38 @@ BN_NOINLINE int hash_to_g1(fq* hx, fq* hy, const uint8_t* msg, uint64_t len, int
   return ST_HASH_TO_POINT;
 }
 
+// One try of the loop above for a message that shares a single SHA-256 block with its counter byte and the padding
+// (len <= 54): used by the compacting batch kernels, where every surviving item of round r tries counter r.
+BN_NOINLINE bool hash_try_1blk(fq* hx, fq* hy, const uint8_t* msg, uint32_t len, uint32_t ctr) {
+  uint32_t blk[16], st[8];
+#pragma unroll
+  for (int i = 0; i < 16; i++) blk[i] = 0;
+  for (uint32_t i = 0; i < len; i++) blk[i >> 2] |= (uint32_t)msg[i] << (24 - 8 * (i & 3));
+  blk[len >> 2] |= ctr << (24 - 8 * (len & 3));
+  blk[(len + 1) >> 2] |= 0x80u << (24 - 8 * ((len + 1) & 3));
+  blk[15] = (len + 1) * 8;
+  sha256_init(st);
+  sha256_compress(st, blk);
+  fq x;
+  for (int i = 0; i < 8; i++) x.l[i] = st[7 - i];
+  if (u256_geq(x.l, K_FIVE_Q)) return false;
+  for (int k = 0; k < 4; k++) {  // mod_u256: while x > q { x -= q }
+    uint32_t t[8];
+    bool gt = !u256_geq(K_Q, x.l);
+    if (gt) {
+      u256_sub(t, x.l, K_Q);
+      for (int i = 0; i < 8; i++) x.l[i] = t[i];
+    }
+  }
+  if (u256_geq(x.l, K_Q)) return false;
+  fq xm = fq_to_mont(x);
+  fq t = fq_add(fq_mul(fq_sqr(xm), xm), fq_from_limbs(K_THREE));
+  fq y;
+  if (!fq_sqrt(&y, t)) return false;
+  if (fq_parity(y)) y = fq_neg(y);
+  *hx = xm;
+  *hy = y;
+  return true;
+}
+
 }  // namespace bn

@@ -357,13 +357,54 @@ def prog_miller(pairs):
     return p
 
 
+def wnaf(n, w):
+    d = []
+    while n:
+        if n & 1:
+            z = n % (1 << (w + 1))
+            if z >= (1 << w):
+                z -= 1 << (w + 1)
+            d.append(z)
+            n -= z
+        else:
+            d.append(0)
+        n //= 2
+    return d
+
+
+EXP_TMP_SLOT = 6  # global slot that holds base^3 during an exponentiation
+
+
 def prog_exp_neg_u(p, base_slot):
-    """P <- conj(P^u) with P == G[base_slot] on entry (S is loaded with the base and stays put)"""
+    """P <- conj(P^u) with P == G[base_slot] on entry.  Signed digits {+-1, +-3} of u (18 non-zero instead of the 28 one
+    bits): in the cyclotomic subgroup the inverse is the conjugate, so a negative digit multiplies by the conjugated table
+    entry (LOADS with the conjugation flag).  S is reloaded only when the table entry or its sign changes."""
+    MUL = ins("DOT", PLAN_ID["MUL"])
+    CYC = ins("DOT", PLAN_ID["CYCLO"])
+    digs = wnaf(U, 2)
+    assert sum(d << i for i, d in enumerate(digs)) == U and set(abs(d) for d in digs if d) <= {1, 3}
+    # base^3 = base^2 * base -> G[EXP_TMP_SLOT]
+    p.append(CYC)
     p.append(ins("LOADS", base_slot))
-    for i in range(61, -1, -1):
-        p.append(ins("DOT", PLAN_ID["CYCLO"]))
-        if (U >> i) & 1:
-            p.append(ins("DOT", PLAN_ID["MUL"]))
+    p.append(MUL)
+    p.append(ins("STORE", EXP_TMP_SLOT))
+    slot_of = {1: base_slot, 3: EXP_TMP_SLOT}
+    top = digs[-1]
+    assert top > 0
+    if top == 3:
+        cur = None          # P already holds base^3
+    else:
+        p.append(ins("LOADP", base_slot))
+        cur = None
+    in_s = (1, False)       # S holds base (loaded above), not conjugated
+    for d in reversed(digs[:-1]):
+        p.append(CYC)
+        if d:
+            want = (abs(d), d < 0)
+            if want != in_s:
+                p.append(ins("LOADS", slot_of[want[0]] | (CONJ_FLAG if want[1] else 0)))
+                in_s = want
+            p.append(MUL)
     p.append(ins("CONJP"))
 
 
@@ -503,6 +544,7 @@ def gen_tables():
     o.append("enum { " + ", ".join("COP_%s = %d" % (n, i) for i, n in enumerate(OPS)) + " };")
     o.append("enum { " + ", ".join("CPLAN_%s = %d" % (n, i) for i, (n, _) in enumerate(PLANS)) + ", CPLAN_COUNT = %d };" % len(PLANS))
     o.append("#define COOP_CONJ_FLAG 0x%02x" % CONJ_FLAG)
+    o.append("#define COOP_GSLOTS %d" % (EXP_TMP_SLOT + 1))
     o.append("#define COOP_DEST_NONE %d" % DEST_NONE)
     o.append("// plan row: word 0 = n | dest << 12 | post << 16 ; words 1..6 = X slot | Y slot << 8 | double X << 16 | negate X << 17")
     o.append("BN_CONST uint32_t K_COOP_PLANS[CPLAN_COUNT][6][7] = {")

@@ -100,6 +100,16 @@ def test_hash_to_g1_random_fixed_len(E):
     assert st == est and out == eout
 
 
+def test_hash_to_g1_compacting_path_lengths(E):
+    """Batches of >= 4096 single-block messages go through the compacting rounds (k_hash_round / k_hash_tail); smaller or
+    longer ones through the per-thread loop.  Both must give the oracle's points, at the block-boundary lengths too."""
+    for msg_len, n in ((0, 4096), (1, 4100), (31, 5000), (54, 4097), (55, 4096), (64, 4096), (32, 4095)):
+        msgs = synth.messages(n, msg_len, seed=100 + msg_len) if msg_len else b""
+        out, st = E.hash_to_g1_batch(msgs, msg_len, n)
+        eout, est = O.hash_to_g1_batch(msgs, msg_len, n, NTHREADS)
+        assert st == est and out == eout, (msg_len, n)
+
+
 def test_hash_to_g1_ragged(E):
     rng = random.Random(3)
     lens = [0, 1, 3, 31, 32, 33, 54, 55, 56, 62, 63, 64, 65, 118, 119, 120, 127, 128, 129, 300, 1000]
