@@ -175,14 +175,35 @@ BN_FN fq fq_sub(const fq& a, const fq& b) {
 #endif
 BN_FN fq fq_dbl(const fq& a) { return fq_add(a, a); }
 // conditional subtraction: a in [0, 2^256) -> a - q if a >= q else a
+#if defined(__CUDA_ARCH__)
+BN_FN fq fq_csub(const fq& a) {
+  uint32_t t0, t1, t2, t3, t4, t5, t6, t7, bw;
+  asm("sub.cc.u32 %0, %9, 0xd87cfd47;\n\t"
+      "subc.cc.u32 %1, %10, 0x3c208c16;\n\t"
+      "subc.cc.u32 %2, %11, 0x6871ca8d;\n\t"
+      "subc.cc.u32 %3, %12, 0x97816a91;\n\t"
+      "subc.cc.u32 %4, %13, 0x8181585d;\n\t"
+      "subc.cc.u32 %5, %14, 0xb85045b6;\n\t"
+      "subc.cc.u32 %6, %15, 0xe131a029;\n\t"
+      "subc.cc.u32 %7, %16, 0x30644e72;\n\t"
+      "subc.u32 %8, 0, 0;\n\t"
+      : "=&r"(t0), "=&r"(t1), "=&r"(t2), "=&r"(t3), "=&r"(t4), "=&r"(t5), "=&r"(t6), "=&r"(t7), "=&r"(bw)
+      : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]));
+  fq r;
+  const bool keep = bw != 0;  // borrow: a < q
+  r.l[0] = keep ? a.l[0] : t0; r.l[1] = keep ? a.l[1] : t1; r.l[2] = keep ? a.l[2] : t2; r.l[3] = keep ? a.l[3] : t3;
+  r.l[4] = keep ? a.l[4] : t4; r.l[5] = keep ? a.l[5] : t5; r.l[6] = keep ? a.l[6] : t6; r.l[7] = keep ? a.l[7] : t7;
+  return r;
+}
+#else
 BN_FN fq fq_csub(const fq& a) {
   fq t;
   const uint32_t qq[8] = {BN_Q0, BN_Q1, BN_Q2, BN_Q3, BN_Q4, BN_Q5, BN_Q6, BN_Q7};
   uint32_t bw = u256_sub(t.l, a.l, qq);
-#pragma unroll
   for (int i = 0; i < 8; i++) t.l[i] = bw ? a.l[i] : t.l[i];
   return t;
 }
+#endif
 BN_FN fq fq_neg(const fq& a) { return fq_sub(fq_zero(), a); }
 
 // ------------------------------------------------------------------------------------------------ Montgomery product

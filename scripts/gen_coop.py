@@ -115,7 +115,7 @@ def gen_mac():
     o.append("BN_FN void wide_mac(uint64_t (&E)[8], uint64_t (&O)[8], uint32_t (&C)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) {\n")
     rows(o, lambda j: "a[%d]" % j, lambda i: "b[%d]" % i)
     o.append("}\n\n")
-    o.append("// Montgomery reduction of the accumulator: returns T / 2^256 mod q in [0, q).  Requires T < 6.2 q^2.\n")
+    o.append("// Montgomery reduction of the accumulator: returns a value congruent to T / 2^256, below T / 2^256 + q.  Requires T < 6.2 q^2.\n")
     o.append("// The rows m_i * q are added exactly like product rows (a = q, b = m_i); the true low limb of round i is\n")
     o.append("// E.limb[i] + O.limb[i-1] + c, c being the carry of the limb below (which the round before made zero).\n")
     o.append("BN_FN fq wide_redc(uint64_t (&E)[8], uint64_t (&O)[8], uint32_t (&C)[8]) {\n")
@@ -145,11 +145,11 @@ def gen_mac():
 
     o.append(addchain("e", lambda k: "p[%d]" % k))
     # counters: C[j] -> limb 8+2j of E = e[2j] ; C[4+j] -> index 8+2j of O = p[2j+1] -> e[2j+1]
+    o.append("  C[0] += c;  // a counter holds at most a few dozen\n")
     o.append(addchain("e", lambda k: "C[%d]" % (k // 2) if k % 2 == 0 else "C[%d]" % (4 + k // 2)))
-    o.append(addchain("e", lambda k: "c" if k == 0 else "0"))
     o.append("  fq r;\n")
     o.append("#pragma unroll\n  for (int k = 0; k < 8; k++) r.l[k] = e[k];\n")
-    o.append("  r = fq_csub(r);\n  r = fq_csub(r);\n  return r;\n}\n")
+    o.append("  return r;  // not yet canonical: the caller subtracts q once or twice\n}\n")
     o.append("#else\n")
     o.append("""// portable form (host simulation): the whole accumulator lives in E as 16 limbs
 BN_FN uint32_t wide_limb(const uint64_t (&E)[8], int w) { return (uint32_t)(E[w >> 1] >> (32 * (w & 1))); }
@@ -180,8 +180,6 @@ BN_FN fq wide_redc(uint64_t (&E)[8], uint64_t (&O)[8], uint32_t (&C)[8]) {
   for (int i = 0; i < 8; i++) wide_row(E, i, K_Q, wide_limb(E, i) * K_QINV_NEG);
   fq r;
   for (int k = 0; k < 8; k++) r.l[k] = wide_limb(E, 8 + k);
-  r = fq_csub(r);
-  r = fq_csub(r);
   return r;
 }
 """)
@@ -197,17 +195,15 @@ DEST_NONE = 15
 POST_NONE, POST_CYC_MINUS, POST_CYC_PLUS = 0, 1, 2
 
 
-F_DBL, F_NEG = 1 << 16, 1 << 17
-
-
 def row(entries=(), dbl_upto=0, neg_from=7, dest=DEST_NONE, post=POST_NONE):
     """entries: (X slot, Y slot); the first dbl_upto entries count twice, entries from neg_from on are subtracted
     (the machine doubles / negates the X operand as it loads it)"""
-    es = []
-    for i, (x, y) in enumerate(entries):
-        es.append(x | (y << 8) | (F_DBL if i < dbl_upto else 0) | (F_NEG if i >= neg_from else 0))
+    es = list(entries)
     assert len(es) <= 6
-    return dict(n=len(es), dest=dest, post=post, e=es)
+    dbl = sum(1 << i for i in range(len(es)) if i < dbl_upto)
+    neg = sum(1 << i for i in range(len(es)) if i >= neg_from)
+    weight = len(es) + min(dbl_upto, len(es))
+    return dict(n=len(es), dbl=dbl, neg=neg, dest=dest, post=post, e=es, weight=weight)
 
 
 def plan_mul():
@@ -484,7 +480,7 @@ def plan_info():
         xi = set()
         for r in rows_:
             for e in r["e"]:
-                for slot in (e & 0xff, (e >> 8) & 0xff):
+                for slot in e:
                     if slot < 36 and slot % 6 == 3:
                         xi.add(slot // 6)
         writes_p = any(r["dest"] < 6 for r in rows_)
@@ -546,14 +542,15 @@ def gen_tables():
     o.append("#define COOP_CONJ_FLAG 0x%02x" % CONJ_FLAG)
     o.append("#define COOP_GSLOTS %d" % (EXP_TMP_SLOT + 1))
     o.append("#define COOP_DEST_NONE %d" % DEST_NONE)
-    o.append("// plan row: word 0 = n | dest << 12 | post << 16 ; words 1..6 = X slot | Y slot << 8 | double X << 16 | negate X << 17")
+    o.append("// plan row: word 0 = n | double-X mask << 4 | negate-X mask << 10 | dest << 16 | post << 20 | (weight <= 3) << 24 ;")
+    o.append("// words 1..6 = byte offset of the X triple | byte offset of the Y triple << 16 (slot * 1024)")
     o.append("BN_CONST uint32_t K_COOP_PLANS[CPLAN_COUNT][6][7] = {")
     for name, fn in PLANS:
         rows = fn()
         o.append("  {  // %s" % name)
         for r in rows:
-            w0 = r["n"] | (r["dest"] << 12) | (r["post"] << 16)
-            es = ["0x%05x" % e for e in r["e"]] + ["0"] * (6 - len(r["e"]))
+            w0 = r["n"] | (r["dbl"] << 4) | (r["neg"] << 10) | (r["dest"] << 16) | (r["post"] << 20) | ((1 if r["weight"] <= 3 else 0) << 24)
+            es = ["0x%08x" % ((x * 1024) | ((y * 1024) << 16)) for x, y in r["e"]] + ["0"] * (6 - len(r["e"]))
             o.append("    {0x%05x, %s}," % (w0, ", ".join(es)))
         o.append("  },")
     o.append("};")
