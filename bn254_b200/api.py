@@ -201,3 +201,42 @@ def check_public_keys(public_key_g2, public_key_g1):
     """/root/reference/src/ecdsa.rs:78-93."""
     st = E.check_public_keys_batch(public_key_g2.raw, public_key_g1.raw)
     _check(st[0])
+
+
+# ---------------------------------------------------------------------------------------------- precompile input formatters
+# /root/reference/src/utils.rs:197-239.  Output = [(G1 64 B, G2 128 B); 2] in the dependency's Borsh form: every 32-byte
+# coordinate little-endian, G1 = x || y, G2 = x.re || x.im || y.re || y.im (this is exactly what the reference's
+# `_uncompressed_` variant produces by reversing each 32-byte chunk of the crate's big-endian uncompressed bytes,
+# :223-229).  No reference test covers these functions: parity is unpinned (SURVEY.md 8f row 2).
+NEG_G2_UNCOMPRESSED = bytes.fromhex(
+    "1800deef121f1e76426a00665e5c4479674322d4f75edadd46debd5cd992f6ed"
+    "198e9393920d483a7260bfb731fb5d25f1aa493335a9e71297e485b7aef312c2"
+    "1d9befcd05a5323e6da4d435f3b617cdb3af83285c2df711ef39c01571827f9d"
+    "275dc4a288d1afb3cbb1ac09187524c7db36395df7be3b99e673b13a075a65ec")
+
+
+def _le_chunks(b):
+    return b"".join(b[i:i + 32][::-1] for i in range(0, len(b), 32))
+
+
+def _pairing_check_values(message, sig_raw, pk_raw):
+    message = bytes(message)
+    h, st = E.hash_to_g1_batch(message if message else None, len(message), 1)
+    _check(st[0])
+    return [(_le_chunks(h), _le_chunks(pk_raw)), (_le_chunks(sig_raw), _le_chunks(NEG_G2_UNCOMPRESSED))]
+
+
+def format_pairing_check_values(message, signature, public_key):
+    """(message, 33-byte compressed signature, 65-byte compressed public key) -> [(H(m), pk), (sig, -G2)]"""
+    pk = PublicKey.from_compressed(public_key)
+    sig = Signature.from_compressed(signature)
+    return _pairing_check_values(message, sig.to_uncompressed(), pk.to_uncompressed())
+
+
+def format_pairing_check_uncompressed_values(message, signature, public_key):
+    """(message, 64-byte uncompressed signature, 128-byte uncompressed public key); like the reference, the point bytes
+    are re-ordered without being validated (/root/reference/src/utils.rs:218-239)."""
+    signature, public_key = bytes(signature), bytes(public_key)
+    if len(signature) != 64 or len(public_key) != 128:
+        raise Error(5)  # the reference's try_into fails with the Vec<u8> -> InvalidLength mapping (src/error.rs:64-68)
+    return _pairing_check_values(message, signature, public_key)

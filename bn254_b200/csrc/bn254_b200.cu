@@ -282,7 +282,10 @@ __global__ void __launch_bounds__(BN_BLOCK) k_item_op(const uint8_t* __restrict_
 
 // ---- cooperative pairing path (coop.cuh): per-item line sets, then six warps per 32 items run the table-driven program
 // H == NULL: the first G1 argument is the generator (check_public_keys)
-__global__ void __launch_bounds__(BN_BLOCK) k_verify_lines(const g1aff* __restrict__ H, const uint8_t* __restrict__ sigs,
+#ifndef BN_LINES_MINB
+#define BN_LINES_MINB 4
+#endif
+__global__ void __launch_bounds__(BN_BLOCK, BN_LINES_MINB) k_verify_lines(const g1aff* __restrict__ H, const uint8_t* __restrict__ sigs,
                                                            const uint8_t* __restrict__ pks, size_t n, u4* __restrict__ lines, size_t n_pad,
                                                            uint8_t* __restrict__ status, const line_t* __restrict__ table) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -295,7 +298,8 @@ __global__ void __launch_bounds__(BN_BLOCK) k_verify_lines(const g1aff* __restri
     h.x = fq_from_limbs(K_G1_GEN_X);
     h.y = fq_from_limbs(K_G1_GEN_Y);
   }
-  status[i] = (uint8_t)item_verify_lines(lines, n_pad, i, &h, sigs + 64 * i, pks + 128 * i, table);
+  __shared__ lines_consts consts[BN_BLOCK];
+  status[i] = (uint8_t)item_verify_lines(lines, n_pad, i, &h, sigs + 64 * i, pks + 128 * i, table, &consts[threadIdx.x]);
 }
 
 #if defined(COOP_ABLATE_NOBAR)  // timing experiment only: results are wrong without the barriers
@@ -733,7 +737,9 @@ static int verify_dev_impl(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, 
   const size_t CHUNK = coop ? ((size_t)1 << 17) : ((size_t)1 << 20);
   size_t cap = n < CHUNK ? n : CHUNK;
   size_t cap_pad = (cap + COOP_LANES - 1) / COOP_LANES * COOP_LANES;
-  DALLOC(H, sizeof(g1aff) * cap);
+  // the hash runs once over the whole batch: its compacting rounds are latency-bound when a round gets small, so one
+  // pass over n items costs far less than n / CHUNK passes over CHUNK items
+  DALLOC(H, sizeof(g1aff) * (msgs ? n : 1));
   DALLOC(F, coop ? 16 : sizeof(fq12) * cap);
   DALLOC(LN, coop ? sizeof(u4) * 2 * COOP_LINE_FQ * 2 * K_N_LINES * cap_pad : 16);
   DALLOC(GS, coop ? sizeof(u4) * COOP_GSLOTS * 6 * 2 * 2 * cap_pad : 16);
@@ -750,9 +756,11 @@ static int verify_dev_impl(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, 
     };
     CK(mark());
     if (msgs) {
-      h = H.as<g1aff>();
-      int rc = hash_dev(ctx, msgs + off * msg_len, msg_len, nullptr, m, h, status + off, nullptr);
-      if (rc) return rc;
+      if (off == 0) {
+        int rc = hash_dev(ctx, msgs, msg_len, nullptr, n, H.as<g1aff>(), status, nullptr);
+        if (rc) return rc;
+      }
+      h = H.as<g1aff>() + off;
     }
     CK(mark());
     if (coop) {

@@ -11,65 +11,111 @@
 
 namespace bn {
 
-BN_FN void coop_emit_scaled(u4* lines, size_t set, size_t n_pad, size_t item, bool use, const line_t* c, const fq* px, const fq* py) {
-  struct {
-    fq2 l0, l3, l4;
-  } L;
-  if (use) {
-    L.l0 = c->ell_0;
-    fq2_scale(&L.l3, &c->ell_vw, py);  // position c1.c1 = w^3
-    fq2_scale(&L.l4, &c->ell_vv, px);  // position c0.c2 = w^4
-  } else {
-    L.l0 = fq2_one();
-    L.l3 = fq2_zero();
-    L.l4 = fq2_zero();
-  }
-  coop_emit_line(lines, set, n_pad, item, L.l0, L.l3, L.l4);
+// the two curve steps of pairing.cuh with every Fq2 value passed in registers (same formulas, same results)
+BN_FN void doubling_step_v(fq2& rx, fq2& ry, fq2& rz, fq2& ell_0, fq2& ell_vw, fq2& ell_vv) {
+  const fq two_inv = fq_from_limbs(K_TWO_INV);
+  const fq2 twist_b = fq2_from_limbs(K_TWIST_B);
+  fq2 a = fq2_scale_v(fq2_mul_v(rx, ry), two_inv);
+  fq2 b = fq2_sqr_v(ry);
+  fq2 cc = fq2_sqr_v(rz);
+  fq2 e = fq2_mul_v(twist_b, fq2_add(fq2_dbl(cc), cc));
+  fq2 f = fq2_add(fq2_dbl(e), e);
+  fq2 g = fq2_scale_v(fq2_add(b, f), two_inv);
+  fq2 h = fq2_sub(fq2_sqr_v(fq2_add(ry, rz)), fq2_add(b, cc));
+  fq2 j = fq2_sqr_v(rx);
+  fq2 e2 = fq2_sqr_v(e);
+  rx = fq2_mul_v(a, fq2_sub(b, f));
+  ry = fq2_sub(fq2_sqr_v(g), fq2_add(fq2_dbl(e2), e2));
+  rz = fq2_mul_v(b, h);
+  ell_0 = fq2_mul_xi(fq2_sub(e, b));
+  ell_vw = fq2_neg(h);
+  ell_vv = fq2_add(fq2_dbl(j), j);
+}
+BN_FN void mixed_addition_step_v(const fq2& qx, const fq2& qy, fq2& rx, fq2& ry, fq2& rz, fq2& ell_0, fq2& ell_vw, fq2& ell_vv) {
+  fq2 d = fq2_sub(rx, fq2_mul_v(qx, rz));
+  fq2 e = fq2_sub(ry, fq2_mul_v(qy, rz));
+  fq2 f = fq2_sqr_v(d);
+  fq2 g = fq2_sqr_v(e);
+  fq2 h = fq2_mul_v(d, f);
+  fq2 i = fq2_mul_v(rx, f);
+  fq2 j = fq2_sub(fq2_add(h, fq2_mul_v(rz, g)), fq2_dbl(i));
+  fq2 t = fq2_mul_v(h, ry);
+  rx = fq2_mul_v(d, j);
+  ry = fq2_sub(fq2_mul_v(e, fq2_sub(i, j)), t);
+  rz = fq2_mul_v(rz, h);
+  ell_0 = fq2_mul_xi(fq2_sub(fq2_mul_v(e, qx), fq2_mul_v(d, qy)));
+  ell_vv = fq2_neg(e);
+  ell_vw = d;
 }
 
-// returns the decode status of (sig, pk); on ST_OK all 174 line sets of the item are written
-BN_NOINLINE int item_verify_lines(u4* lines, size_t n_pad, size_t item, const g1aff* h, const uint8_t* sig, const uint8_t* pk,
-                                  const line_t* table) {
-  struct {
+// per-thread constants of the walk, kept in shared memory on the device (registers are for the running point):
+// [0] qx  [1] qy  [2] (hx, hy)  [3] (sx, sy)
+struct lines_consts {
+  fq2 v[4];
+};
+
+BN_FN void coop_emit_scaled_v(u4* lines, size_t set, size_t n_pad, size_t item, bool use, const fq2& ell_0, const fq2& ell_vw, const fq2& ell_vv,
+                              const fq2& pxy) {
+  fq2 l0, l3, l4;
+  if (use) {
+    l0 = ell_0;
+    l3 = fq2_scale_v(ell_vw, pxy.c1);  // position c1.c1 = w^3, scaled by the G1 point's y
+    l4 = fq2_scale_v(ell_vv, pxy.c0);  // position c0.c2 = w^4, scaled by the G1 point's x
+  } else {
+    l0 = fq2_one();
+    l3 = fq2_zero();
+    l4 = fq2_zero();
+  }
+  coop_emit_line(lines, set, n_pad, item, l0, l3, l4);
+}
+
+// returns the decode status of (sig, pk); on ST_OK all 174 line sets of the item are written.  K points at this thread's
+// constants block (shared memory on the device).
+BN_FN int item_verify_lines(u4* lines, size_t n_pad, size_t item, const g1aff* h, const uint8_t* sig, const uint8_t* pk, const line_t* table,
+                            lines_consts* K) {
+  bool use_a, use_b;
+  {
     g2j q;
     g1j s;
-    g2proj r;
-    line_t c;
-    fq2 qy_sel, q1x, q1y, q2x, q2y;
-  } L;
-  int st = g2_from_raw(&L.q, pk);
-  if (st) return st;
-  st = g1_from_raw(&L.s, sig);
-  if (st) return st;
-  const bool use_a = !pt_is_inf(&L.q), use_b = !pt_is_inf(&L.s);
-  L.r.x = L.q.x;
-  L.r.y = L.q.y;
-  L.r.z = fq2_one();
+    int st = g2_from_raw(&q, pk);
+    if (st) return st;
+    st = g1_from_raw(&s, sig);
+    if (st) return st;
+    use_a = !pt_is_inf(&q);
+    use_b = !pt_is_inf(&s);
+    K->v[0] = q.x;
+    K->v[1] = q.y;
+    K->v[2].c0 = h->x;
+    K->v[2].c1 = h->y;
+    K->v[3].c0 = s.x;
+    K->v[3].c1 = s.y;
+  }
+  fq2 rx = K->v[0], ry = K->v[1], rz = fq2_one();
+  fq2 c0 = fq2_one(), cvw = fq2_zero(), cvv = fq2_zero();
   size_t m = 0;
+#pragma unroll 1
   for (int k = 0; k < 64; k++) {
-    if (use_a) doubling_step(&L.r, &L.c);
-    coop_emit_scaled(lines, 2 * m, n_pad, item, use_a, &L.c, &h->x, &h->y);
-    coop_emit_scaled(lines, 2 * m + 1, n_pad, item, use_b, &table[m], &L.s.x, &L.s.y);
+    if (use_a) doubling_step_v(rx, ry, rz, c0, cvw, cvv);
+    coop_emit_scaled_v(lines, 2 * m, n_pad, item, use_a, c0, cvw, cvv, K->v[2]);
+    coop_emit_scaled_v(lines, 2 * m + 1, n_pad, item, use_b, table[m].ell_0, table[m].ell_vw, table[m].ell_vv, K->v[3]);
     m++;
-    int d = K_ATE_DIGITS[k];
+    const int d = K_ATE_DIGITS[k];
     if (d != 0) {
-      if (use_a) {
-        L.qy_sel = d > 0 ? L.q.y : fq2_neg(L.q.y);
-        mixed_addition_step(&L.q.x, &L.qy_sel, &L.r, &L.c);
-      }
-      coop_emit_scaled(lines, 2 * m, n_pad, item, use_a, &L.c, &h->x, &h->y);
-      coop_emit_scaled(lines, 2 * m + 1, n_pad, item, use_b, &table[m], &L.s.x, &L.s.y);
+      if (use_a) mixed_addition_step_v(K->v[0], d > 0 ? K->v[1] : fq2_neg(K->v[1]), rx, ry, rz, c0, cvw, cvv);
+      coop_emit_scaled_v(lines, 2 * m, n_pad, item, use_a, c0, cvw, cvv, K->v[2]);
+      coop_emit_scaled_v(lines, 2 * m + 1, n_pad, item, use_b, table[m].ell_0, table[m].ell_vw, table[m].ell_vv, K->v[3]);
       m++;
     }
   }
-  if (use_a) g2_frobenius_pair(&L.q1x, &L.q1y, &L.q2x, &L.q2y, L.q.x, L.q.y);
-  if (use_a) mixed_addition_step(&L.q1x, &L.q1y, &L.r, &L.c);
-  coop_emit_scaled(lines, 2 * m, n_pad, item, use_a, &L.c, &h->x, &h->y);
-  coop_emit_scaled(lines, 2 * m + 1, n_pad, item, use_b, &table[m], &L.s.x, &L.s.y);
+  fq2 q1x, q1y, q2x, q2y;
+  g2_frobenius_pair(&q1x, &q1y, &q2x, &q2y, K->v[0], K->v[1]);
+  if (use_a) mixed_addition_step_v(q1x, q1y, rx, ry, rz, c0, cvw, cvv);
+  coop_emit_scaled_v(lines, 2 * m, n_pad, item, use_a, c0, cvw, cvv, K->v[2]);
+  coop_emit_scaled_v(lines, 2 * m + 1, n_pad, item, use_b, table[m].ell_0, table[m].ell_vw, table[m].ell_vv, K->v[3]);
   m++;
-  if (use_a) mixed_addition_step(&L.q2x, &L.q2y, &L.r, &L.c);
-  coop_emit_scaled(lines, 2 * m, n_pad, item, use_a, &L.c, &h->x, &h->y);
-  coop_emit_scaled(lines, 2 * m + 1, n_pad, item, use_b, &table[m], &L.s.x, &L.s.y);
+  if (use_a) mixed_addition_step_v(q2x, q2y, rx, ry, rz, c0, cvw, cvv);
+  coop_emit_scaled_v(lines, 2 * m, n_pad, item, use_a, c0, cvw, cvv, K->v[2]);
+  coop_emit_scaled_v(lines, 2 * m + 1, n_pad, item, use_b, table[m].ell_0, table[m].ell_vw, table[m].ell_vv, K->v[3]);
   return ST_OK;
 }
 

@@ -124,6 +124,29 @@ BN_NOINLINE void fq2_scale(fq2* r, const fq2* a, const fq* s) {
   r->c0 = x;
   r->c1 = y;
 }
+// by-value forms (register ABI on the device): for callers that keep their working set in registers
+BN_FQ2_LEAF fq2 fq2_mul_v(fq2 a, fq2 b) {
+  fq aa = fq_mul(a.c0, b.c0);
+  fq bb = fq_mul(a.c1, b.c1);
+  fq s = fq_mul(fq_add(a.c0, a.c1), fq_add(b.c0, b.c1));
+  fq2 r;
+  r.c0 = fq_sub(aa, bb);
+  r.c1 = fq_sub(fq_sub(s, aa), bb);
+  return r;
+}
+BN_FQ2_LEAF fq2 fq2_sqr_v(fq2 a) {
+  fq m = fq_mul(a.c0, a.c1);
+  fq2 r;
+  r.c0 = fq_mul(fq_add(a.c0, a.c1), fq_sub(a.c0, a.c1));
+  r.c1 = fq_dbl(m);
+  return r;
+}
+BN_FQ2_LEAF fq2 fq2_scale_v(fq2 a, fq k) {
+  fq2 r;
+  r.c0 = fq_mul(a.c0, k);
+  r.c1 = fq_mul(a.c1, k);
+  return r;
+}
 // value-returning forms: operands are copied into call-local slots (by-value parameters) so that every memory
 // temporary lives only around its own call
 BN_FN fq2 fq2_mulv(fq2 a, fq2 b) {

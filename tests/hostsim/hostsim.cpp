@@ -223,7 +223,8 @@ API int hs_coop_verify(const uint8_t* msg, size_t len, const uint8_t* sig, const
     if (st) return st;
   }
   coop_sim S;
-  int st = item_verify_lines(S.lines.data(), S.n_pad, 0, &h, sig, pk, g_lines);
+  lines_consts K;
+  int st = item_verify_lines(S.lines.data(), S.n_pad, 0, &h, sig, pk, g_lines, &K);
   if (st) return st;
   S.run(K_COOP_PROG_VERIFY);
   return S.status;
@@ -235,7 +236,8 @@ API int hs_coop_verify_miller(const uint8_t* msg, size_t len, const uint8_t* sig
   int st = hash_to_g1(&h.x, &h.y, msg, len, nullptr);
   if (st) return st;
   coop_sim S;
-  st = item_verify_lines(S.lines.data(), S.n_pad, 0, &h, sig, pk, g_lines);
+  lines_consts K;
+  st = item_verify_lines(S.lines.data(), S.n_pad, 0, &h, sig, pk, g_lines, &K);
   if (st) return st;
   S.run(K_COOP_PROG_MILLER2);
   fq12 f;

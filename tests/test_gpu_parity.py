@@ -471,3 +471,21 @@ def test_pairing_modes_agree_on_ragged_batches(E):
         st = E.check_public_keys_batch(bytes(pk2), pk1, ctx=ctx)
         assert st[3] == O.VERIFICATION_FAILED and st[7] != 0 and sum(1 for s in st if s == 0) == 38, (mode, st)
     ctx.call("bn254_set_pairing_mode", I(0))
+
+
+def test_format_pairing_check_values(E):
+    """/root/reference/src/utils.rs:197-239 has no reference test (parity unpinned): check the two formatters against each
+    other, the little-endian layout against the oracle's points, and that the formatted pairs satisfy the pairing check."""
+    from bn254_b200 import (ECDSA, PrivateKey, PublicKey, format_pairing_check_uncompressed_values, format_pairing_check_values)
+    v = G["verify_ok"][0]
+    sk = PrivateKey(H(v["sk"]))
+    pk = PublicKey.from_private_key(sk)
+    msg = H(v["msg"])
+    sig = ECDSA.sign(msg, sk)
+    a = format_pairing_check_values(msg, sig.to_compressed(), pk.to_compressed())
+    b = format_pairing_check_uncompressed_values(msg, sig.to_uncompressed(), pk.to_uncompressed())
+    assert a == b and [len(x) for p in a for x in p] == [64, 128, 64, 128]
+    rev = lambda x: b"".join(x[i:i + 32][::-1] for i in range(0, len(x), 32))
+    assert rev(a[0][0]) == O.hash_to_g1(msg)[1] and rev(a[0][1]) == pk.to_uncompressed()
+    assert rev(a[1][0]) == sig.to_uncompressed() and rev(a[1][1]) == O.g2_neg(O.derive_pk_g2(be(1))[1])[1]
+    assert E.pairing_check_batch(rev(a[0][0]) + rev(a[1][0]), rev(a[0][1]) + rev(a[1][1]), 2, 1) == b"\x00"
