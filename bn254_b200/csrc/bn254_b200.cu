@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(BN_BLOCK, BN_LINES_MINB) k_verify_lines(const 
 #define BN_COOP_MINB 4
 #endif
 // which: 0 verify (Miller of 2 line streams + final exponentiation + verdict), 1 / 2 Miller of 1 / 2 streams -> fio,
-// 3 final exponentiation of fio (+ verdict)
+// 3 final exponentiation of fio (+ verdict), 4 multi-pairing: COOP_MULTI_K pairs per lane, block product -> fio
 __global__ void __launch_bounds__(COOP_THREADS, BN_COOP_MINB) k_coop_run(int which, size_t n, size_t n_pad, const u4* __restrict__ lines,
                                                                          u4* __restrict__ gslots, u4* __restrict__ fio,
                                                                          uint8_t* __restrict__ status) {
@@ -327,16 +327,59 @@ __global__ void __launch_bounds__(COOP_THREADS, BN_COOP_MINB) k_coop_run(int whi
   c.gslots = gslots;
   c.fio = fio;
   c.status = status;
-  const uint32_t* prog = which == 0 ? K_COOP_PROG_VERIFY : which == 1 ? K_COOP_PROG_MILLER1 : which == 2 ? K_COOP_PROG_MILLER2 : K_COOP_PROG_FINALEXP;
+  const uint32_t* prog = which == 0 ? K_COOP_PROG_VERIFY : which == 1 ? K_COOP_PROG_MILLER1 : which == 2 ? K_COOP_PROG_MILLER2 : which == 3 ? K_COOP_PROG_FINALEXP : K_COOP_PROG_MULTI;
+  int line_next = 0;
 #pragma unroll 1
   for (int pc = 0;; pc++) {
     const uint32_t ins = prog[pc];
     if ((ins & 0xff) == COP_END) break;
-    fq2 t = coop_phase_a(c, ins);
+    fq2 t = coop_phase_a(c, ins, line_next);
     COOP_BARRIER();
-    coop_phase_b(c, ins, t);
+    coop_phase_b(c, ins, t, line_next);
     COOP_BARRIER();
   }
+}
+
+// ---- multi-pairing through the cooperative machine: pair p is stream p / L of lane p % L (L lanes, COOP_MULTI_K streams each)
+__device__ __forceinline__ void record_error(unsigned long long* err, size_t i, int st);
+__global__ void __launch_bounds__(BN_BLOCK, BN_LINES_MINB) k_pair_lines(const g1aff* __restrict__ H, const uint8_t* __restrict__ hstatus,
+                                                                        const uint8_t* __restrict__ pks, size_t n, size_t L,
+                                                                        u4* __restrict__ lines, unsigned long long* __restrict__ err,
+                                                                        size_t index_base) {
+  __shared__ lines_consts consts[BN_BLOCK];
+  size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= L * COOP_MULTI_K) return;
+  bool use = false;
+  g1aff h;
+  g2j q;
+  q.x = fq2_one();
+  q.y = fq2_one();
+  if (p < n) {
+    if (hstatus[p]) {
+      record_error(err, index_base + p, hstatus[p]);
+    } else {
+      int st = g2_from_raw(&q, pks + 128 * p);
+      if (st) record_error(err, index_base + p, st);
+      else if (!pt_is_inf(&q)) {
+        use = true;
+        h = H[p];
+      }
+    }
+  }
+  item_pair_lines(lines, L, p % L, (int)(p / L), use, &h, q.x, q.y, &consts[threadIdx.x]);
+}
+// lane 0 of every block holds the block's product (power-basis layout fio) -> tower-order Fq12 array
+__global__ void k_coop_gather(const u4* __restrict__ fio, size_t L, size_t blocks, fq12* __restrict__ out) {
+  size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= blocks) return;
+  const int pos[6] = {0, 2, 4, 1, 3, 5};
+  fq12 f;
+  fq2* c = &f.c0.c0;
+  for (int t = 0; t < 6; t++) {
+    c[t].c0 = coop_gld(fio, (size_t)pos[t] * 2 + 0, L, b * COOP_LANES);
+    c[t].c1 = coop_gld(fio, (size_t)pos[t] * 2 + 1, L, b * COOP_LANES);
+  }
+  out[b] = f;
 }
 
 // ---- point aggregation: strided mixed additions per thread, then a shared-memory tree per block
@@ -1014,6 +1057,32 @@ static int distinct_partial_dev(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_
   CK(cudaMemsetAsync(err.p, 0xff, 8, ctx->stream));
   int rc = hash_dev(ctx, msgs, msg_len, nullptr, n, H.as<g1aff>(), hst.as<uint8_t>(), nullptr);
   if (rc) return rc;
+  if (ctx->pairing_mode == 0 && n > 0) {
+    // cooperative multi-pairing: chunks of 2^20 pairs (26 GB of line sets), every block leaves one partial product
+    const size_t CH = (size_t)1 << 20;
+    const size_t per_block = (size_t)COOP_LANES * COOP_MULTI_K;
+    size_t total_blocks = 0;
+    for (size_t off = 0; off < n; off += CH) total_blocks += ((n - off < CH ? n - off : CH) + per_block - 1) / per_block;
+    size_t capn = n < CH ? n : CH;
+    size_t capL = (capn + per_block - 1) / per_block * COOP_LANES;
+    DALLOC(LN, sizeof(u4) * COOP_MULTI_K * COOP_LINE_FQ * 2 * K_N_LINES * capL);
+    DALLOC(FIO, sizeof(u4) * 6 * 2 * 2 * capL);
+    DALLOC(partial, sizeof(fq12) * total_blocks);
+    size_t done_blocks = 0;
+    for (size_t off = 0; off < n; off += CH) {
+      size_t m = n - off < CH ? n - off : CH;
+      size_t blocks = (m + per_block - 1) / per_block, L = blocks * COOP_LANES;
+      LAUNCH(k_pair_lines, grid_for(L * COOP_MULTI_K), BN_BLOCK, H.as<g1aff>() + off, hst.as<uint8_t>() + off, pks + 128 * off, m, L, LN.as<u4>(),
+             err.as<unsigned long long>(), off);
+      k_coop_run<<<(unsigned)blocks, COOP_THREADS, COOP_SMEM_BYTES, ctx->stream>>>(4, L, L, LN.as<u4>(), (u4*)nullptr, FIO.as<u4>(), (uint8_t*)nullptr);
+      ctx->launches++;
+      CK(cudaGetLastError());
+      LAUNCH(k_coop_gather, grid_for(blocks), BN_BLOCK, FIO.as<u4>(), L, blocks, partial.as<fq12>() + done_blocks);
+      done_blocks += blocks;
+    }
+    LAUNCH(k_fq12_prod_final, 1, BN_PROD_BLOCK, partial.as<fq12>(), (int)total_blocks, (fq12*)nullptr, f_be, err.as<unsigned long long>(), status);
+    return 0;
+  }
   size_t max_blocks = (size_t)ctx->sm_count * 4;
   size_t blocks = (n + BN_PROD_BLOCK - 1) / BN_PROD_BLOCK;
   if (blocks > max_blocks) blocks = max_blocks;

@@ -290,7 +290,7 @@ PLANS = [("MUL", plan_mul), ("SQR", plan_sqr), ("SPARSE_A", lambda: plan_sparse(
          ("INV_C", plan_inv_c)]
 
 # ------------------------------------------------------------------------------------------------ programs
-OPS = ["END", "DOT", "LINE", "LOADP", "LOADS", "STORE", "COPY_PS_CONJ", "CONJP", "FROBP", "INVT", "ONE", "CHECK", "LOADF", "STOREF"]
+OPS = ["END", "DOT", "LINE", "LOADP", "LOADS", "STORE", "COPY_PS_CONJ", "CONJP", "FROBP", "INVT", "ONE", "CHECK", "LOADF", "STOREF", "XLANE"]
 OPC = {n: i for i, n in enumerate(OPS)}
 PLAN_ID = {n: i for i, (n, _) in enumerate(PLANS)}
 CONJ_FLAG = 0x80
@@ -306,10 +306,10 @@ ATE = [1, 0, 1, 0, 0, 0, -1, 0, -1, 0, 0, 0, -1, 0, 1, 0, -1, 0, 0, -1, 0, 0, 0,
 U = 4965661367192848881
 
 
-def dot(plan, prefetch=None, buf=0):
-    """DOT instruction; prefetch = line set to fetch into S buffer `buf` while the dot product runs"""
-    a2 = 0 if prefetch is None else ((prefetch + 1) | (buf << 8))
-    return ins("DOT", PLAN_ID[plan], a2)
+def dot(plan, prefetch=False):
+    """DOT instruction; prefetch: fetch the next line set (a running counter in the machine; set m goes to S buffer m & 1)
+    while the dot product runs"""
+    return ins("DOT", PLAN_ID[plan], 1 if prefetch else 0)
 
 
 def prog_miller(pairs):
@@ -345,11 +345,24 @@ def prog_miller(pairs):
         else:
             m = o[1]
             assert m <= fetched
-            pf = None
+            pf = False
             if m == fetched and nxt is not None:
-                pf = nxt
+                pf = True
                 fetched = nxt
-            p.append(dot("SPARSE_A" if m % 2 == 0 else "SPARSE_B", pf, (pf or 0) & 1))
+            p.append(dot("SPARSE_A" if m % 2 == 0 else "SPARSE_B", pf))
+    return p
+
+
+MULTI_K = 8  # pairs per lane in the multi-pairing program (they share one squaring chain)
+
+
+def prog_multi_miller(k):
+    """Every lane folds k pairs into one Miller value (shared squarings), then the 32 lanes of the block are multiplied
+    together by a butterfly: S <- P of lane ^ s, P <- S * P for s = 16, 8, 4, 2, 1.  Every lane ends with the block's product."""
+    p = prog_miller(k)
+    for sft in (16, 8, 4, 2, 1):
+        p.append(ins("XLANE", sft))
+        p.append(ins("DOT", PLAN_ID["MUL"]))
     return p
 
 
@@ -541,6 +554,7 @@ def gen_tables():
     o.append("enum { " + ", ".join("CPLAN_%s = %d" % (n, i) for i, (n, _) in enumerate(PLANS)) + ", CPLAN_COUNT = %d };" % len(PLANS))
     o.append("#define COOP_CONJ_FLAG 0x%02x" % CONJ_FLAG)
     o.append("#define COOP_GSLOTS %d" % (EXP_TMP_SLOT + 1))
+    o.append("#define COOP_MULTI_K %d" % MULTI_K)
     o.append("#define COOP_DEST_NONE %d" % DEST_NONE)
     o.append("// plan row: word 0 = n | double-X mask << 4 | negate-X mask << 10 | dest << 16 | post << 20 | (weight <= 3) << 24 ;")
     o.append("// words 1..6 = byte offset of the X triple | byte offset of the Y triple << 16 (slot * 1024)")
@@ -557,6 +571,7 @@ def gen_tables():
     for name, prog0 in (("VERIFY", prog_miller(2) + prog_final_exp() + [ins("CHECK"), ins("END")]),
                        ("MILLER1", prog_miller(1) + [ins("STOREF"), ins("END")]),
                        ("MILLER2", prog_miller(2) + [ins("STOREF"), ins("END")]),
+                       ("MULTI", prog_multi_miller(MULTI_K) + [ins("STOREF"), ins("END")]),
                        ("FINALEXP", [ins("LOADF")] + prog_final_exp() + [ins("STOREF"), ins("CHECK"), ins("END")])):
         prog = add_xi_skip(prog0)
         o.append("#define K_COOP_PROG_%s_LEN %d" % (name, len(prog)))

@@ -176,21 +176,25 @@ struct coop_sim {
   std::vector<u4> sm, lines, gslots, fio;
   uint8_t status = 0;
   size_t n_pad = COOP_LANES;
-  coop_sim() : sm(COOP_SLOTS * 2 * COOP_LANES), lines((size_t)2 * K_N_LINES * COOP_LINE_FQ * 2 * COOP_LANES),
+  coop_sim() : sm(COOP_SLOTS * 2 * COOP_LANES), lines((size_t)COOP_MULTI_K * K_N_LINES * COOP_LINE_FQ * 2 * COOP_LANES),
                gslots((size_t)COOP_GSLOTS * 6 * 2 * 2 * COOP_LANES), fio((size_t)6 * 2 * 2 * COOP_LANES) {}
-  coop_ctx ctx(int k) {
+  int lanes = 1;  // simulated lanes of the block (32 for the multi-pairing butterfly)
+  int line_next[COOP_WARPS][COOP_LANES] = {};
+  coop_ctx ctx(int k, int lane) {
     coop_ctx c;
-    c.sm = sm.data(); c.k = k; c.lane = 0; c.active = true; c.item = 0; c.n_pad = n_pad;
+    c.sm = sm.data(); c.k = k; c.lane = lane; c.active = true; c.item = lane; c.n_pad = n_pad;
     c.lines = lines.data(); c.gslots = gslots.data(); c.fio = fio.data(); c.status = &status;
     return c;
   }
   void run(const uint32_t* prog) {
+    std::vector<fq2> t(COOP_WARPS * COOP_LANES);
     for (int pc = 0;; pc++) {
       uint32_t ins = prog[pc];
       if ((ins & 0xff) == COP_END) break;
-      fq2 t[COOP_WARPS];
-      for (int k = 0; k < COOP_WARPS; k++) t[k] = coop_phase_a(ctx(k), ins);
-      for (int k = 0; k < COOP_WARPS; k++) coop_phase_b(ctx(k), ins, t[k]);
+      for (int l = 0; l < lanes; l++)
+        for (int k = 0; k < COOP_WARPS; k++) t[k * COOP_LANES + l] = coop_phase_a(ctx(k, l), ins, line_next[k][l]);
+      for (int l = 0; l < lanes; l++)
+        for (int k = 0; k < COOP_WARPS; k++) coop_phase_b(ctx(k, l), ins, t[k * COOP_LANES + l], line_next[k][l]);
     }
   }
   // tower order c0.c0, c0.c1, c0.c2, c1.c0, c1.c1, c1.c2 <- a0, a2, a4, a1, a3, a5
@@ -280,5 +284,37 @@ API int hs_coop_plan(int plan, const uint8_t* p_in, const uint8_t* s_in, uint8_t
   S.run(prog);
   S.get_fio(&r);
   fq12_to_be(out, &r);
+  return 0;
+}
+
+// multi-pairing program: n <= 32 * COOP_MULTI_K pairs (g1 64 B, g2 128 B each) -> the block's Miller product (tower order)
+API int hs_coop_multi_miller(const uint8_t* g1s, const uint8_t* g2s, size_t n, uint8_t* f_out) {
+  coop_sim S;
+  S.lanes = COOP_LANES;
+  lines_consts K;
+  for (size_t slot = 0; slot < (size_t)COOP_LANES * COOP_MULTI_K; slot++) {
+    size_t lane = slot % COOP_LANES;
+    int stream = (int)(slot / COOP_LANES);
+    bool use = false;
+    g1aff h;
+    g2j q;
+    q.x = fq2_one();
+    q.y = fq2_one();
+    if (slot < n) {
+      g1j p;
+      int st = g1_from_raw(&p, g1s + 64 * slot);
+      if (st) return st;
+      st = g2_from_raw(&q, g2s + 128 * slot);
+      if (st) return st;
+      use = !pt_is_inf(&p) && !pt_is_inf(&q);
+      h.x = p.x;
+      h.y = p.y;
+    }
+    item_pair_lines(S.lines.data(), S.n_pad, lane, stream, use, &h, q.x, q.y, &K);
+  }
+  S.run(K_COOP_PROG_MULTI);
+  fq12 f;
+  S.get_fio(&f);
+  fq12_to_be(f_out, &f);
   return 0;
 }

@@ -489,3 +489,31 @@ def test_format_pairing_check_values(E):
     assert rev(a[0][0]) == O.hash_to_g1(msg)[1] and rev(a[0][1]) == pk.to_uncompressed()
     assert rev(a[1][0]) == sig.to_uncompressed() and rev(a[1][1]) == O.g2_neg(O.derive_pk_g2(be(1))[1])[1]
     assert E.pairing_check_batch(rev(a[0][0]) + rev(a[1][0]), rev(a[0][1]) + rev(a[1][1]), 2, 1) == b"\x00"
+
+
+def test_distinct_partial_modes_bit_identical(E):
+    """The Miller product of a slice of (H(m_i), pk_i) pairs is a canonical field value: the cooperative multi-pairing program
+    (8 pairs per lane, block butterfly) and the one-thread-per-pair kernels must return the same 384 bytes, and the oracle's."""
+    from bn254_b200._native import I
+    ctx = E.context(0)
+    n = 777  # not a multiple of 8 * 32: padding slots carry constant-1 lines
+    msgs, sks, sigs, pks = _signed_set(E, n, seed=91)
+    pks = bytearray(pks)
+    pks[128 * 13:128 * 14] = bytes(128)  # a pair with an infinite G2 point is skipped
+    pks = bytes(pks)
+    got = {}
+    for mode in (0, 1):
+        ctx.call("bn254_set_pairing_mode", I(mode))
+        got[mode] = E.miller_partial_distinct(msgs, 32, pks, ctx=ctx)
+    ctx.call("bn254_set_pairing_mode", I(0))
+    assert got[0] == got[1] and got[0][1] == 0
+    hs = E.hash_to_g1_batch(msgs, 32, n, ctx=ctx)[0]
+    assert got[0][0] == O.miller_product(hs, pks, n)[1]
+    # a bad key in the slice: first error by index, in both modes
+    bad = bytearray(pks)
+    bad[128 * 500 + 127] ^= 1
+    for mode in (0, 1):
+        ctx.call("bn254_set_pairing_mode", I(mode))
+        assert E.miller_partial_distinct(msgs, 32, bytes(bad), ctx=ctx)[1] == O.INVALID_GROUP_POINT
+    ctx.call("bn254_set_pairing_mode", I(0))
+    assert E.miller_partial_distinct(b"", 32, b"", ctx=ctx)[0] == be(1) + bytes(352)

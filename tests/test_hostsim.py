@@ -270,3 +270,16 @@ def test_coop_verify_matches_oracle(hs):
         assert hs.hs_coop_verify(b"", 0, O.derive_pk_g1(H(v["sk"]))[1], O.derive_pk_g2(H(v["sk"]))[1], 1) == 0
     for v in G["check_public_keys_fail"]:
         assert hs.hs_coop_verify(b"", 0, O.derive_pk_g1(H(v["sk_g1"]))[1], O.derive_pk_g2(H(v["sk_g2"]))[1], 1) == O.VERIFICATION_FAILED
+
+
+def test_coop_multi_pairing_program(hs):
+    """COOP_MULTI_K pairs per lane share one squaring chain, then the 32 lanes are multiplied by a butterfly: the block's
+    product equals the oracle's Miller product over all pairs (canonical field values, any multiplication order)."""
+    rng = random.Random(17)
+    n = 41  # lanes 0..31 hold stream 0, lanes 0..8 also stream 1; the other slots are padding (constant-1 lines)
+    g1s = b"".join(O.derive_pk_g1(be(rng.randrange(1, R)))[1] for _ in range(n))
+    g2s = b"".join(O.derive_pk_g2(be(rng.randrange(1, R)))[1] for _ in range(n))
+    g1s = g1s[:64 * 5] + bytes(64) + g1s[64 * 6:]      # one pair with an infinite G1 point: skipped
+    f = buf(384)
+    assert hs.hs_coop_multi_miller(g1s, g2s, n, f) == 0
+    assert f.raw == O.miller_product(g1s, g2s, n)[1]
