@@ -30,6 +30,13 @@ using namespace bn;
 #endif
 
 // ------------------------------------------------------------------------------------------------ kernels
+// fixed-base tables of the two generators: one thread per window row
+__global__ void k_init_comb(aff<fq>* t1, aff<fq2>* t2) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= BN_COMB_WINDOWS) return;
+  comb_build_row(t1 + w * BN_COMB_ROW, w, fq_from_limbs(K_G1_GEN_X), fq_from_limbs(K_G1_GEN_Y));
+  comb_build_row(t2 + w * BN_COMB_ROW, w, fq2_from_limbs(K_G2_GEN_X), fq2_from_limbs(K_G2_GEN_Y));
+}
 __global__ void k_init_lines(line_t* out) {
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     fq2 gx = fq2_from_limbs(K_G2_GEN_X), gy = fq2_neg(fq2_from_limbs(K_G2_GEN_Y));
@@ -265,8 +272,8 @@ __global__ void __launch_bounds__(BN_BLOCK) k_item_op(const uint8_t* __restrict_
   int st = ST_OK;
   if (OP == OP_G1_MUL) st = item_g1_mul(out + 64 * i, a + 64 * i, b + 32 * i);
   else if (OP == OP_G2_MUL) st = item_g2_mul(out + 128 * i, a + 128 * i, b + 32 * i);
-  else if (OP == OP_DERIVE_G1) item_derive_pk_g1(out + 64 * i, a + 32 * i);
-  else if (OP == OP_DERIVE_G2) item_derive_pk_g2(out + 128 * i, a + 32 * i);
+  else if (OP == OP_DERIVE_G1) item_derive_pk_g1_comb(out + 64 * i, a + 32 * i, (const aff<fq>*)b);   // b = the context's G1 table
+  else if (OP == OP_DERIVE_G2) item_derive_pk_g2_comb(out + 128 * i, a + 32 * i, (const aff<fq2>*)b);  // b = the context's G2 table
   else if (OP == OP_G1_COMPRESS) {
     st = item_g1_compress(out + 33 * i, a + 64 * i);
     if (st) for (int k = 0; k < 33; k++) out[33 * i + k] = 0;
@@ -542,6 +549,8 @@ struct bn254_ctx {
   int sm_count = 0;
   cudaStream_t stream = nullptr;
   line_t* d_lines = nullptr;
+  aff<fq>* d_comb_g1 = nullptr;   // (d + 1) * 16^w * G1 generator
+  aff<fq2>* d_comb_g2 = nullptr;  // (d + 1) * 16^w * G2 generator
   uint64_t launches = 0;
   int pairing_mode = 0;  // 0: cooperative six-warp machine (coop.cuh), 1: one thread per item (pairing.cuh)
   std::string err;
@@ -613,7 +622,12 @@ int bn254_ctx_create(int device, bn254_ctx** out) {
   k_init_lines<<<1, 1, 0, ctx->stream>>>(ctx->d_lines);
   ctx->launches++;
   if ((e = cudaGetLastError()) != cudaSuccess) return fail("k_init_lines launch", e);
-  if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return fail("k_init_lines", e);
+  if ((e = cudaMalloc(&ctx->d_comb_g1, sizeof(aff<fq>) * BN_COMB_WINDOWS * BN_COMB_ROW)) != cudaSuccess) return fail("cudaMalloc(comb g1)", e);
+  if ((e = cudaMalloc(&ctx->d_comb_g2, sizeof(aff<fq2>) * BN_COMB_WINDOWS * BN_COMB_ROW)) != cudaSuccess) return fail("cudaMalloc(comb g2)", e);
+  k_init_comb<<<2, 32, 0, ctx->stream>>>(ctx->d_comb_g1, ctx->d_comb_g2);
+  ctx->launches++;
+  if ((e = cudaGetLastError()) != cudaSuccess) return fail("k_init_comb launch", e);
+  if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return fail("k_init_lines / k_init_comb", e);
   if ((e = cudaFuncSetAttribute(k_coop_run, cudaFuncAttributeMaxDynamicSharedMemorySize, COOP_SMEM_BYTES)) != cudaSuccess)
     return fail("cudaFuncSetAttribute(k_coop_run)", e);
   *out = ctx;
@@ -625,6 +639,8 @@ void bn254_ctx_destroy(bn254_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->d_lines) cudaFree(ctx->d_lines);
+  if (ctx->d_comb_g1) cudaFree(ctx->d_comb_g1);
+  if (ctx->d_comb_g2) cudaFree(ctx->d_comb_g2);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -998,7 +1014,7 @@ int bn254_fq12_op_batch(bn254_ctx* ctx, int op, const uint8_t* a384, const uint8
 // generic host wrapper of k_item_op
 template <int OP>
 static int item_op_host(bn254_ctx* ctx, const uint8_t* a, size_t a_bytes, const uint8_t* b, size_t b_bytes, size_t n, uint8_t* out,
-                        size_t out_bytes, uint8_t* status) {
+                        size_t out_bytes, uint8_t* status, const void* dev_b = nullptr) {
   ENTER();
   if (n == 0) return 0;
   ARGCHECK(a != nullptr && (b_bytes == 0 || b != nullptr));
@@ -1008,7 +1024,9 @@ static int item_op_host(bn254_ctx* ctx, const uint8_t* a, size_t a_bytes, const 
   DALLOC(d_st, n);
   H2D(d_a.p, a, a_bytes * n);
   if (b_bytes) H2D(d_b.p, b, b_bytes * n);
-  LAUNCH(k_item_op<OP>, grid_for(n), BN_BLOCK, d_a.as<uint8_t>(), d_b.as<uint8_t>(), n, d_out.as<uint8_t>(), d_st.as<uint8_t>());
+  // dev_b: a device-resident second operand (the context's fixed-base table) instead of per-item host bytes
+  LAUNCH(k_item_op<OP>, grid_for(n), BN_BLOCK, d_a.as<uint8_t>(), dev_b ? (const uint8_t*)dev_b : d_b.as<uint8_t>(), n, d_out.as<uint8_t>(),
+         d_st.as<uint8_t>());
   if (out && out_bytes) D2H(out, d_out.p, out_bytes * n);
   if (status) D2H(status, d_st.p, n);
   CK(cudaStreamSynchronize(ctx->stream));
@@ -1103,10 +1121,10 @@ int bn254_g2_mul_batch(bn254_ctx* ctx, const uint8_t* pts, const uint8_t* scalar
   return item_op_host<OP_G2_MUL>(ctx, pts, 128, scalars, 32, n, out128, 128, status);
 }
 int bn254_derive_pk_g1_batch(bn254_ctx* ctx, const uint8_t* sks, size_t n, uint8_t* out64) {
-  return item_op_host<OP_DERIVE_G1>(ctx, sks, 32, nullptr, 0, n, out64, 64, nullptr);
+  return item_op_host<OP_DERIVE_G1>(ctx, sks, 32, nullptr, 0, n, out64, 64, nullptr, ctx ? ctx->d_comb_g1 : nullptr);
 }
 int bn254_derive_pk_g2_batch(bn254_ctx* ctx, const uint8_t* sks, size_t n, uint8_t* out128) {
-  return item_op_host<OP_DERIVE_G2>(ctx, sks, 32, nullptr, 0, n, out128, 128, nullptr);
+  return item_op_host<OP_DERIVE_G2>(ctx, sks, 32, nullptr, 0, n, out128, 128, nullptr, ctx ? ctx->d_comb_g2 : nullptr);
 }
 int bn254_g1_compress_batch(bn254_ctx* ctx, const uint8_t* raw64, size_t n, uint8_t* out33, uint8_t* status) {
   return item_op_host<OP_G1_COMPRESS>(ctx, raw64, 64, nullptr, 0, n, out33, 33, status);

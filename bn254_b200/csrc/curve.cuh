@@ -177,6 +177,40 @@ BN_NOINLINE void pt_mul(jac<F>* r, const jac<F>* p, const uint32_t* k) {
   *r = acc;
 }
 
+// ---- fixed-base scalar multiplication (key derivation, /root/reference/src/types.rs:85-87,155-157): a table of
+// d * 16^w * G (w = 0..63, d = 1..15, affine) turns G * k into at most 64 mixed additions and no doubling.
+template <class F>
+struct alignas(16) aff {
+  F x, y;
+};
+#define BN_COMB_WINDOWS 64
+#define BN_COMB_ROW 15
+// row w of the table: entries (d + 1) * 16^w * G for d = 0..14
+template <class F>
+BN_FN void comb_build_row(aff<F>* row, int w, const F& gx, const F& gy) {
+  jac<F> base, acc;
+  pt_set_affine(&base, gx, gy);
+  for (int i = 0; i < 4 * w; i++) pt_dbl(&base, &base);
+  acc = base;
+  for (int d = 0; d < BN_COMB_ROW; d++) {
+    if (d) pt_add(&acc, &acc, &base);
+    pt_to_affine(&row[d].x, &row[d].y, &acc);  // never infinity: 16^w * (d + 1) < r
+  }
+}
+template <class F>
+BN_NOINLINE void pt_mul_fixed(jac<F>* r, const aff<F>* table, const uint32_t* k) {
+  jac<F> acc;
+  pt_set_inf(&acc);
+  for (int w = 0; w < BN_COMB_WINDOWS; w++) {
+    uint32_t nib = (k[w >> 3] >> ((w & 7) * 4)) & 15;
+    if (nib) {
+      aff<F> t = table[w * BN_COMB_ROW + nib - 1];
+      pt_madd(&acc, &acc, &t.x, &t.y);
+    }
+  }
+  *r = acc;
+}
+
 // curve membership (affine): y^2 == x^3 + b
 BN_FN bool g1_on_curve(const fq& x, const fq& y) {
   fq l = fq_sqr(y);

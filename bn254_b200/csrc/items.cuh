@@ -80,6 +80,22 @@ BN_FN void item_derive_pk_g2(uint8_t* out, const uint8_t* sk_be) {
   g2_to_raw(out, &s);
 }
 
+// the same through the fixed-base tables (device path; the ladder above stays as the table-free cross-check)
+BN_FN void item_derive_pk_g1_comb(uint8_t* out, const uint8_t* sk_be, const aff<fq>* table) {
+  uint32_t k[8];
+  fr_reduce(k, sk_be);
+  g1j s;
+  pt_mul_fixed(&s, table, k);
+  g1_to_raw(out, &s);
+}
+BN_FN void item_derive_pk_g2_comb(uint8_t* out, const uint8_t* sk_be, const aff<fq2>* table) {
+  uint32_t k[8];
+  fr_reduce(k, sk_be);
+  g2j s;
+  pt_mul_fixed(&s, table, k);
+  g2_to_raw(out, &s);
+}
+
 // ---------------------------------------------------------------------------------------------- verify
 // /root/reference/src/ecdsa.rs:49-64 after the hash: decode pk (G2) and sig (G1), skip pairs holding an infinity,
 // f = miller(H, pk) * miller(sig, -G2).  Returns the decode status; on ST_OK *f is the Miller product.

@@ -318,3 +318,18 @@ API int hs_coop_multi_miller(const uint8_t* g1s, const uint8_t* g2s, size_t n, u
   fq12_to_be(f_out, &f);
   return 0;
 }
+
+// fixed-base tables (curve.cuh comb_build_row / pt_mul_fixed), built on the host exactly as k_init_comb does on the device
+static aff<fq> g_comb1[BN_COMB_WINDOWS * BN_COMB_ROW];
+static aff<fq2> g_comb2[BN_COMB_WINDOWS * BN_COMB_ROW];
+static bool g_comb_init = false;
+static void ensure_comb() {
+  if (g_comb_init) return;
+  for (int w = 0; w < BN_COMB_WINDOWS; w++) {
+    comb_build_row(g_comb1 + w * BN_COMB_ROW, w, fq_from_limbs(K_G1_GEN_X), fq_from_limbs(K_G1_GEN_Y));
+    comb_build_row(g_comb2 + w * BN_COMB_ROW, w, fq2_from_limbs(K_G2_GEN_X), fq2_from_limbs(K_G2_GEN_Y));
+  }
+  g_comb_init = true;
+}
+API void hs_derive_pk_g1_comb(const uint8_t* sk, uint8_t* out) { ensure_comb(); item_derive_pk_g1_comb(out, sk, g_comb1); }
+API void hs_derive_pk_g2_comb(const uint8_t* sk, uint8_t* out) { ensure_comb(); item_derive_pk_g2_comb(out, sk, g_comb2); }

@@ -283,3 +283,20 @@ def test_coop_multi_pairing_program(hs):
     f = buf(384)
     assert hs.hs_coop_multi_miller(g1s, g2s, n, f) == 0
     assert f.raw == O.miller_product(g1s, g2s, n)[1]
+
+
+def test_fixed_base_tables(hs):
+    """G * sk through the 64 x 15 fixed-base tables == the ladder == the oracle, incl. the reference's key KATs, keys > r
+    (reduced mod r like Fr::from_slice), 0, 1, r - 1 and scalars with zero nibbles."""
+    for v in G["sk_to_pk_g2"]:
+        out = buf(128)
+        hs.hs_derive_pk_g2_comb(H(v["sk"]), out)
+        assert out.raw == H(v["pk_uncompressed"])
+    rng = random.Random(23)
+    sks = [be(0), be(1), be(R - 1), be(R), be(R + 5), be((1 << 256) - 1), be(0x10000000000000000000000000000f00), be(15 << 252)]
+    sks += [H(s) for s in G["example"]["sks"]] + [be(rng.randrange(1 << 256)) for _ in range(12)]
+    for sk in sks:
+        o1, o2 = buf(64), buf(128)
+        hs.hs_derive_pk_g1_comb(sk, o1)
+        hs.hs_derive_pk_g2_comb(sk, o2)
+        assert o1.raw == O.derive_pk_g1(sk)[1] and o2.raw == O.derive_pk_g2(sk)[1], sk.hex()
