@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -317,6 +318,9 @@ __global__ void __launch_bounds__(BN_BLOCK, BN_LINES_MINB) k_verify_lines(const 
 #ifndef BN_COOP_MINB
 #define BN_COOP_MINB 4
 #endif
+#ifndef BN_COOP_DEFAULT_W
+#define BN_COOP_DEFAULT_W false
+#endif
 // which: 0 verify (Miller of 2 line streams + final exponentiation + verdict), 1 / 2 Miller of 1 / 2 streams -> fio,
 // 3 final exponentiation of fio (+ verdict), 4 multi-pairing: COOP_MULTI_K pairs per lane, block product -> fio
 __global__ void __launch_bounds__(COOP_THREADS, BN_COOP_MINB) k_coop_run(int which, size_t n, size_t n_pad, const u4* __restrict__ lines,
@@ -324,9 +328,12 @@ __global__ void __launch_bounds__(COOP_THREADS, BN_COOP_MINB) k_coop_run(int whi
                                                                          uint8_t* __restrict__ status) {
   extern __shared__ u4 coop_sm[];
   coop_ctx c;
-  c.sm = coop_sm;
   c.k = threadIdx.x >> 5;
   c.lane = threadIdx.x & 31;
+  c.sm = coop_sm + c.lane;
+  c.row = COOP_LANES;
+  c.wmode = false;
+  c.plans = K_COOP_PLANS;
   c.item = (size_t)blockIdx.x * COOP_LANES + c.lane;
   c.active = c.item < n;
   c.n_pad = n_pad;
@@ -344,6 +351,60 @@ __global__ void __launch_bounds__(COOP_THREADS, BN_COOP_MINB) k_coop_run(int whi
     COOP_BARRIER();
     coop_phase_b(c, ins, t, line_next);
     COOP_BARRIER();
+  }
+}
+
+// ---- warp-local form of the same machine: the six coefficients of an item live in six lanes of ONE warp (lane = 5 k + j,
+// five items per warp, lanes 30 and 31 idle), so the two synchronisation points of an instruction are __syncwarp() and
+// no warp ever waits for a sibling that shares its sub-partition with other blocks.  The only block-level step is the
+// single Fq inversion of the final exponentiation: the block's 30 items are gathered into one warp between two block
+// barriers.  Shared memory: 54 slots x 160 B per warp, plus the plan table (lane-varying index, so not constant memory).
+#define COOPW_WARPS 6
+#define COOPW_ITEMS (COOPW_WARPS * COOPW_ROW)
+#define COOPW_WARP_U4 (COOP_SLOTS * 2 * COOPW_ROW)
+#define COOPW_PLAN_WORDS (CPLAN_COUNT * 6 * 7)
+#define COOPW_SMEM_BYTES (COOPW_WARPS * COOPW_WARP_U4 * 16 + COOPW_PLAN_WORDS * 4)
+__global__ void __launch_bounds__(COOPW_WARPS * 32, BN_COOP_MINB) k_coopw_run(int which, size_t n, size_t n_pad, const u4* __restrict__ lines,
+                                                                              u4* __restrict__ gslots, u4* __restrict__ fio,
+                                                                              uint8_t* __restrict__ status) {
+  extern __shared__ u4 coop_sm[];
+  uint32_t* plans = (uint32_t*)(coop_sm + COOPW_WARPS * COOPW_WARP_U4);
+  for (int i = threadIdx.x; i < COOPW_PLAN_WORDS; i += blockDim.x) plans[i] = (&K_COOP_PLANS_W[0][0][0])[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, L = threadIdx.x & 31;
+  const bool live = L < 6 * COOPW_ROW;
+  coop_ctx c;
+  c.k = live ? L / COOPW_ROW : 0;
+  c.lane = live ? L % COOPW_ROW : 0;
+  c.sm = coop_sm + warp * COOPW_WARP_U4 + c.lane;
+  c.row = COOPW_ROW;
+  c.wmode = true;
+  c.plans = (const uint32_t (*)[6][7])plans;
+  c.item = ((size_t)blockIdx.x * COOPW_WARPS + warp) * COOPW_ROW + c.lane;
+  c.active = live && c.item < n;
+  c.n_pad = n_pad;
+  c.lines = lines;
+  c.gslots = gslots;
+  c.fio = fio;
+  c.status = status;
+  const uint32_t* prog = which == 0 ? K_COOP_PROG_VERIFY : which == 1 ? K_COOP_PROG_MILLER1 : which == 2 ? K_COOP_PROG_MILLER2 : K_COOP_PROG_FINALEXP;
+  int line_next = 0;
+#pragma unroll 1
+  for (int pc = 0;; pc++) {
+    const uint32_t ins = prog[pc];
+    const int op = ins & 0xff;
+    if (op == COP_END) break;
+    if (op == COP_INVT) {
+      __syncthreads();
+      if (warp == 0 && L < COOPW_ITEMS) coop_invt(coop_sm + (L / COOPW_ROW) * COOPW_WARP_U4 + (L % COOPW_ROW), COOPW_ROW);
+      __syncthreads();
+      continue;
+    }
+    fq2 t;
+    if (live) t = coop_phase_a(c, ins, line_next);
+    __syncwarp();
+    if (live) coop_phase_b(c, ins, t, line_next);
+    __syncwarp();
   }
 }
 
@@ -552,7 +613,10 @@ struct bn254_ctx {
   aff<fq>* d_comb_g1 = nullptr;   // (d + 1) * 16^w * G1 generator
   aff<fq2>* d_comb_g2 = nullptr;  // (d + 1) * 16^w * G2 generator
   uint64_t launches = 0;
-  int pairing_mode = 0;  // 0: cooperative six-warp machine (coop.cuh), 1: one thread per item (pairing.cuh)
+  // 0: cooperative machine (coop.cuh) in its default layout, 1: one thread per item (pairing.cuh),
+  // 2: cooperative, block layout (six warps per 32 items), 3: cooperative, warp-local layout (six lanes per item)
+  int pairing_mode = 0;
+  bool coop_w = BN_COOP_DEFAULT_W;  // layout mode 0 uses for verify (BN254_COOP_W=0/1 in the environment overrides)
   std::string err;
   // optional per-phase timing of the verify pipeline (bn254_set_profiling): events recorded on `stream`
   bool prof = false;
@@ -602,6 +666,7 @@ int bn254_ctx_create(int device, bn254_ctx** out) {
   }
   bn254_ctx* ctx = new bn254_ctx();
   ctx->device = device;
+  if (const char* w = getenv("BN254_COOP_W")) ctx->coop_w = w[0] == '1';
   auto fail = [&](const char* what, cudaError_t ee) {
     g_create_err = std::string(what) + ": " + cudaGetErrorString(ee);
     delete ctx;
@@ -630,6 +695,8 @@ int bn254_ctx_create(int device, bn254_ctx** out) {
   if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return fail("k_init_lines / k_init_comb", e);
   if ((e = cudaFuncSetAttribute(k_coop_run, cudaFuncAttributeMaxDynamicSharedMemorySize, COOP_SMEM_BYTES)) != cudaSuccess)
     return fail("cudaFuncSetAttribute(k_coop_run)", e);
+  if ((e = cudaFuncSetAttribute(k_coopw_run, cudaFuncAttributeMaxDynamicSharedMemorySize, COOPW_SMEM_BYTES)) != cudaSuccess)
+    return fail("cudaFuncSetAttribute(k_coopw_run)", e);
   *out = ctx;
   return 0;
 }
@@ -791,9 +858,11 @@ int bn254_sign_batch(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, const 
 // msgs == NULL: check_public_keys form (first G1 argument = generator, no hashing)
 static int verify_dev_impl(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, const uint8_t* sigs, const uint8_t* pks, size_t n,
                            uint8_t* status) {
-  const bool coop = ctx->pairing_mode == 0;
+  const bool coop = ctx->pairing_mode != 1;
+  const bool wl = ctx->pairing_mode == 3 || (ctx->pairing_mode == 0 && ctx->coop_w);
   // chunking bounds the workspace: the cooperative path stores 174 line sets (50 KB) per item
-  const size_t CHUNK = coop ? ((size_t)1 << 17) : ((size_t)1 << 20);
+  // (warp-local layout: a whole number of waves of 30-item blocks, so that the last wave of a chunk is not mostly empty)
+  const size_t CHUNK = !coop ? ((size_t)1 << 20) : wl ? (size_t)ctx->sm_count * BN_COOP_MINB * COOPW_ITEMS * 7 : ((size_t)1 << 17);
   size_t cap = n < CHUNK ? n : CHUNK;
   size_t cap_pad = (cap + COOP_LANES - 1) / COOP_LANES * COOP_LANES;
   // the hash runs once over the whole batch: its compacting rounds are latency-bound when a round gets small, so one
@@ -826,8 +895,12 @@ static int verify_dev_impl(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, 
       size_t m_pad = (m + COOP_LANES - 1) / COOP_LANES * COOP_LANES;
       LAUNCH(k_verify_lines, grid_for(m), BN_BLOCK, h, sigs + 64 * off, pks + 128 * off, m, LN.as<u4>(), m_pad, status + off, ctx->d_lines);
       CK(mark());
-      k_coop_run<<<(unsigned)(m_pad / COOP_LANES), COOP_THREADS, COOP_SMEM_BYTES, ctx->stream>>>(0, m, m_pad, LN.as<u4>(), GS.as<u4>(),
-                                                                                                  (u4*)nullptr, status + off);
+      if (wl)
+        k_coopw_run<<<(unsigned)((m + COOPW_ITEMS - 1) / COOPW_ITEMS), COOPW_WARPS * 32, COOPW_SMEM_BYTES, ctx->stream>>>(
+            0, m, m_pad, LN.as<u4>(), GS.as<u4>(), (u4*)nullptr, status + off);
+      else
+        k_coop_run<<<(unsigned)(m_pad / COOP_LANES), COOP_THREADS, COOP_SMEM_BYTES, ctx->stream>>>(0, m, m_pad, LN.as<u4>(), GS.as<u4>(),
+                                                                                                    (u4*)nullptr, status + off);
       ctx->launches++;
       CK(cudaGetLastError());
       CK(mark());
@@ -842,7 +915,7 @@ static int verify_dev_impl(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, 
 }
 int bn254_set_pairing_mode(bn254_ctx* ctx, int mode) {
   ENTER();
-  ARGCHECK(mode == 0 || mode == 1);
+  ARGCHECK(mode >= 0 && mode <= 3);
   ctx->pairing_mode = mode;
   return 0;
 }
@@ -1075,7 +1148,7 @@ static int distinct_partial_dev(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_
   CK(cudaMemsetAsync(err.p, 0xff, 8, ctx->stream));
   int rc = hash_dev(ctx, msgs, msg_len, nullptr, n, H.as<g1aff>(), hst.as<uint8_t>(), nullptr);
   if (rc) return rc;
-  if (ctx->pairing_mode == 0 && n > 0) {
+  if (ctx->pairing_mode != 1 && n > 0) {
     // cooperative multi-pairing: chunks of 2^20 pairs (26 GB of line sets), every block leaves one partial product
     const size_t CH = (size_t)1 << 20;
     const size_t per_block = (size_t)COOP_LANES * COOP_MULTI_K;

@@ -381,6 +381,7 @@ def wnaf(n, w):
     return d
 
 
+WROW = 5  # items per warp in the warp-local layout (6 coefficients x 5 items = 30 lanes)
 EXP_TMP_SLOT = 6  # global slot that holds base^3 during an exponentiation
 
 
@@ -557,17 +558,20 @@ def gen_tables():
     o.append("#define COOP_MULTI_K %d" % MULTI_K)
     o.append("#define COOP_DEST_NONE %d" % DEST_NONE)
     o.append("// plan row: word 0 = n | double-X mask << 4 | negate-X mask << 10 | dest << 16 | post << 20 | (weight <= 3) << 24 ;")
-    o.append("// words 1..6 = byte offset of the X triple | byte offset of the Y triple << 16 (slot * 1024)")
-    o.append("BN_CONST uint32_t K_COOP_PLANS[CPLAN_COUNT][6][7] = {")
-    for name, fn in PLANS:
-        rows = fn()
-        o.append("  {  // %s" % name)
-        for r in rows:
-            w0 = r["n"] | (r["dbl"] << 4) | (r["neg"] << 10) | (r["dest"] << 16) | (r["post"] << 20) | ((1 if r["weight"] <= 3 else 0) << 24)
-            es = ["0x%08x" % ((x * 1024) | ((y * 1024) << 16)) for x, y in r["e"]] + ["0"] * (6 - len(r["e"]))
-            o.append("    {0x%05x, %s}," % (w0, ", ".join(es)))
-        o.append("  },")
-    o.append("};")
+    o.append("// words 1..6 = byte offset of the X triple | byte offset of the Y triple << 16 (slot * slot bytes: 1024 in the")
+    o.append("// block layout = 32 items per row, %d in the warp-local layout = %d items per row)" % (32 * WROW, WROW))
+    o.append("#define COOPW_ROW %d" % WROW)
+    for tname, slot_bytes in (("K_COOP_PLANS", 1024), ("K_COOP_PLANS_W", 32 * WROW)):
+        o.append("BN_CONST uint32_t %s[CPLAN_COUNT][6][7] = {" % tname)
+        for name, fn in PLANS:
+            rows = fn()
+            o.append("  {  // %s" % name)
+            for r in rows:
+                w0 = r["n"] | (r["dbl"] << 4) | (r["neg"] << 10) | (r["dest"] << 16) | (r["post"] << 20) | ((1 if r["weight"] <= 3 else 0) << 24)
+                es = ["0x%08x" % ((x * slot_bytes) | ((y * slot_bytes) << 16)) for x, y in r["e"]] + ["0"] * (6 - len(r["e"]))
+                o.append("    {0x%05x, %s}," % (w0, ", ".join(es)))
+            o.append("  },")
+        o.append("};")
     for name, prog0 in (("VERIFY", prog_miller(2) + prog_final_exp() + [ins("CHECK"), ins("END")]),
                        ("MILLER1", prog_miller(1) + [ins("STOREF"), ins("END")]),
                        ("MILLER2", prog_miller(2) + [ins("STOREF"), ins("END")]),

@@ -172,17 +172,23 @@ API int hs_layer_op(int op, const uint8_t* in, int n_in, uint8_t* out, int n_out
 #include "../../bn254_b200/csrc/coop_lines.cuh"
 #include <vector>
 
+static int g_coop_wmode = 0;  // 0: block layout (32 items per row, warp k = coefficient k), 1: warp-local layout (5 items per row)
+API void hs_coop_set_layout(int wmode) { g_coop_wmode = wmode; }
+
 struct coop_sim {
   std::vector<u4> sm, lines, gslots, fio;
   uint8_t status = 0;
   size_t n_pad = COOP_LANES;
+  bool wmode = g_coop_wmode != 0;
+  int row = wmode ? COOPW_ROW : COOP_LANES;
   coop_sim() : sm(COOP_SLOTS * 2 * COOP_LANES), lines((size_t)COOP_MULTI_K * K_N_LINES * COOP_LINE_FQ * 2 * COOP_LANES),
                gslots((size_t)COOP_GSLOTS * 6 * 2 * 2 * COOP_LANES), fio((size_t)6 * 2 * 2 * COOP_LANES) {}
-  int lanes = 1;  // simulated lanes of the block (32 for the multi-pairing butterfly)
+  int lanes = 1;  // simulated items of the group (32 for the multi-pairing butterfly, block layout only)
   int line_next[COOP_WARPS][COOP_LANES] = {};
   coop_ctx ctx(int k, int lane) {
     coop_ctx c;
-    c.sm = sm.data(); c.k = k; c.lane = lane; c.active = true; c.item = lane; c.n_pad = n_pad;
+    c.sm = sm.data() + lane; c.row = row; c.wmode = wmode; c.plans = wmode ? K_COOP_PLANS_W : K_COOP_PLANS;
+    c.k = k; c.lane = lane; c.active = true; c.item = lane; c.n_pad = n_pad;
     c.lines = lines.data(); c.gslots = gslots.data(); c.fio = fio.data(); c.status = &status;
     return c;
   }
@@ -191,6 +197,10 @@ struct coop_sim {
     for (int pc = 0;; pc++) {
       uint32_t ins = prog[pc];
       if ((ins & 0xff) == COP_END) break;
+      if (wmode && (ins & 0xff) == COP_INVT) {  // k_coopw_run: the block's items are inverted by one warp between two block barriers
+        for (int l = 0; l < lanes; l++) coop_invt(sm.data() + l, row);
+        continue;
+      }
       for (int l = 0; l < lanes; l++)
         for (int k = 0; k < COOP_WARPS; k++) t[k * COOP_LANES + l] = coop_phase_a(ctx(k, l), ins, line_next[k][l]);
       for (int l = 0; l < lanes; l++)

@@ -217,7 +217,16 @@ def test_codecs(hs):
 
 
 # ---------------------------------------------------------------------------------------------- cooperative machine
-def test_coop_plans_match_tower(hs):
+@pytest.fixture(params=[0, 1], ids=["block-layout", "warp-local-layout"])
+def layout(hs, request):
+    """Both shared-memory layouts of the machine run the same programs: six warps per 32 items (k_coop_run) and six lanes
+    per item, five items per warp (k_coopw_run)."""
+    hs.hs_coop_set_layout(request.param)
+    yield request.param
+    hs.hs_coop_set_layout(0)
+
+
+def test_coop_plans_match_tower(hs, layout):
     """One plan of the six-warp machine == the tower formula of the oracle (product, square, cyclotomic square)."""
     rng = random.Random(11)
     for _ in range(6):
@@ -236,7 +245,7 @@ def test_coop_plans_match_tower(hs):
     assert hs.hs_coop_plan(1, edge, None, out) == 0 and out.raw == O.fq12_op(1, edge)[1]
 
 
-def test_coop_final_exp(hs):
+def test_coop_final_exp(hs, layout):
     rng = random.Random(12)
     for _ in range(3):
         f = rand_fq12(rng)
@@ -246,7 +255,7 @@ def test_coop_final_exp(hs):
         assert st == O.VERIFICATION_FAILED  # a random value does not map to one
 
 
-def test_coop_verify_matches_oracle(hs):
+def test_coop_verify_matches_oracle(hs, layout):
     rng = random.Random(13)
     neg_g2 = O.g2_neg(O.derive_pk_g2(be(1))[1])[1]
     for t in range(4):
