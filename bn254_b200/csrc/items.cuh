@@ -173,10 +173,43 @@ BN_FN int item_g1_validate(const uint8_t* raw) {
   return g1_on_curve(x, y) ? ST_OK : ST_INVALID_GROUP_POINT;
 }
 
-BN_FN bool g2_in_subgroup(const g2j* p) {  // [r]P == infinity, as AffineG2::new does
-  g2j t;
-  pt_mul(&t, p, K_R_ORDER);
-  return pt_is_inf(&t);
+// psi = twist^-1 o Frobenius o twist on Jacobian coordinates: (X, Y, Z) -> (gx conj X, gy conj Y, conj Z),
+// gx = xi^((q-1)/3), gy = xi^((q-1)/2)
+BN_FN void g2_psi(g2j* r, const g2j* p) {
+  fq2 kx = fq2_from_limbs(K_TWIST_MUL_BY_Q_X), ky = fq2_from_limbs(K_TWIST_MUL_BY_Q_Y), t;
+  t = fq2_conj(p->x);
+  fq2_mul(&r->x, &t, &kx);
+  t = fq2_conj(p->y);
+  fq2_mul(&r->y, &t, &ky);
+  r->z = fq2_conj(p->z);
+}
+// r-torsion test of a finite affine point p of the twist (z = 1).  AffineG2::new computes [r]P == infinity
+// [DEP-RECALLED]; the same predicate is decided here with one 63-bit scalar multiplication:
+//     P in G2  <=>  [u+1]P + psi([u]P) + psi^2([u]P) == psi^3([2u]P)
+// (Dai, Lin, Zhao, Zhou, "Fast subgroup membership testings for G1, G2 and GT on pairing-friendly curves", BN case).
+// E'(Fq2) has order r * h2 with h2 = 2q - r = 10069 * 5864401 * 1875725156269 * (a 177-bit prime), all to the first
+// power; psi acts on each prime-order part as a scalar, the left-minus-right polynomial in psi vanishes on the r part
+// and tests/test_oracle.py::test_g2_subgroup_psi_criterion checks that it does not vanish on a point of each of the
+// four prime orders dividing h2, which makes the equivalence exact for this curve (not probabilistic).
+BN_FN bool g2_in_subgroup(const g2j* p) {
+  g2j a, b, c, l, r2;
+  a = *p;
+  for (int i = 61; i >= 0; i--) {  // [u]P, u = K_BN_U (63 bits, top bit consumed by a = P)
+    pt_dbl(&a, &a);
+    if ((K_BN_U >> i) & 1) pt_madd(&a, &a, &p->x, &p->y);
+  }
+  g2_psi(&b, &a);               // psi([u]P)
+  g2_psi(&c, &b);               // psi^2([u]P)
+  pt_madd(&l, &a, &p->x, &p->y);  // [u+1]P
+  pt_add(&l, &l, &b);
+  pt_add(&l, &l, &c);
+  pt_dbl(&r2, &a);              // [2u]P
+  g2_psi(&r2, &r2);
+  g2_psi(&r2, &r2);
+  g2_psi(&r2, &r2);
+  r2.y = fq2_neg(r2.y);
+  pt_add(&l, &l, &r2);
+  return pt_is_inf(&l);
 }
 BN_FN int item_g2_validate(const uint8_t* raw) {
   g2j p;

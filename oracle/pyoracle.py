@@ -201,6 +201,30 @@ def g2_in_subgroup(p):
     return g2_mul(p, R) is None
 
 
+# The engine decides the same predicate with one 63-bit scalar multiplication (bn254_b200/csrc/items.cuh
+# g2_in_subgroup): [u+1]P + psi([u]P) + psi^2([u]P) == psi^3([2u]P), psi = untwist-Frobenius-twist.  Restated here so
+# that tests/test_oracle.py can prove the two predicates equal on E'(Fq2) (one point of every prime order dividing the
+# twist cofactor h2 = 2q - r).
+PSI_X = f2_pow(XI, (Q - 1) // 3)
+PSI_Y = f2_pow(XI, (Q - 1) // 2)
+TWIST_COFACTOR_FACTORS = (10069, 5864401, 1875725156269, 197620364512881247228717050342013327560683201906968909)
+
+
+def g2_psi(p):
+    if p is None:
+        return None
+    (x0, x1), (y0, y1) = p
+    return (f2_mul((x0, (-x1) % Q), PSI_X), f2_mul((y0, (-y1) % Q), PSI_Y))
+
+
+def g2_in_subgroup_psi(p):
+    a = g2_mul(p, U)
+    b = g2_psi(a)
+    c = g2_psi(b)
+    lhs = g2_add(g2_add(g2_add(a, p), b), c)
+    return lhs == g2_psi(g2_psi(g2_psi(g2_add(a, a))))
+
+
 # --------------------------------------------------------------------------- byte formats
 def _be32(x):
     return x.to_bytes(32, "big")

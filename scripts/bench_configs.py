@@ -64,14 +64,21 @@ def main():
     agg, _ = E.g1_sum(sigs[:64 * m5], ctx=ctx)
     v = E.finish_distinct(bytes(d_f.cpu().numpy().tobytes()), agg, ctx=ctx)
     print(json.dumps({"config": "5: distinct-message aggregate verify (Miller partial of %d pairs + shared final exp)" % m5, "pairs_per_sec": m5 / dt, "ms": dt * 1e3, "status": v}))
-    m6 = min(n, 1 << 16)
+    m6 = min(n, 1 << 18)
     comp, st = E.g2_compress_batch(pks[:128 * m6], ctx=ctx)
-    t = time.perf_counter()
-    raw, st = E.g2_decompress_batch(comp, ctx=ctx)
-    dt = time.perf_counter() - t
+    raw, st = E.g2_decompress_batch(comp, ctx=ctx)  # warm
     assert raw == pks[:128 * m6] and not any(st)
-    print(json.dumps({"config": "ingest: G2 from_compressed incl. r-torsion check (host buffers)", "n": m6, "keys_per_sec": m6 / dt, "ms": dt * 1e3}))
-
+    t = time.perf_counter()
+    for _ in range(3):
+        E.g2_decompress_batch(comp, ctx=ctx)
+    dt = (time.perf_counter() - t) / 3
+    print(json.dumps({"config": "ingest: G2 from_compressed incl. Fq2 sqrt and r-torsion check (host buffers)", "n": m6, "keys_per_sec": m6 / dt, "ms": dt * 1e3}))
+    t = time.perf_counter()
+    for _ in range(3):
+        st = E.g2_validate_batch(pks[:128 * m6], ctx=ctx)
+    dt = (time.perf_counter() - t) / 3
+    assert not any(st)
+    print(json.dumps({"config": "ingest: G2 uncompressed validate (curve + r-torsion check, host buffers)", "n": m6, "keys_per_sec": m6 / dt, "ms": dt * 1e3}))
 
 if __name__ == "__main__":
     main()

@@ -330,6 +330,14 @@ def test_codecs(E):
         x += 1
     raw = be(x) + be(0) + be(y[0]) + be(y[1])
     assert E.g2_validate_batch(raw)[0] == O.INVALID_GROUP_POINT
+    import edge_points
+    edge = edge_points.subgroup_edge_points()   # every prime-order part of the twist cofactor, mixed points, cofactor-cleared points
+    got = E.g2_validate_batch(b"".join(pt for pt, _ in edge))
+    assert list(got) == [0 if inside else O.INVALID_GROUP_POINT for _, inside in edge]
+    assert list(got) == [O.g2_validate_uncompressed(pt) for pt, _ in edge]
+    comp = E.g2_compress_batch(b"".join(pt for pt, _ in edge))[0]
+    st = E.g2_decompress_batch(comp)[1]
+    assert list(st) == [0 if inside else O.NOT_MEMBER for _, inside in edge] == [O.g2_decompress(comp[65 * i:65 * i + 65])[0] for i in range(len(edge))]
 
 
 # ---------------------------------------------------------------------------------------------- aggregation

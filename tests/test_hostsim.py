@@ -214,6 +214,10 @@ def test_codecs(hs):
         x += 1
     raw = be(x) + be(0) + be(y[0]) + be(y[1])
     assert hs.hs_g2_validate(raw, 128) == O.INVALID_GROUP_POINT == O.g2_validate_uncompressed(raw)
+    import edge_points
+    for pt, inside in edge_points.subgroup_edge_points():   # small-order components of the twist cofactor, mixed points, cofactor-cleared points
+        want = 0 if inside else O.INVALID_GROUP_POINT
+        assert hs.hs_g2_validate(pt, 128) == want == O.g2_validate_uncompressed(pt)
 
 
 # ---------------------------------------------------------------------------------------------- cooperative machine

@@ -185,3 +185,67 @@ def test_decode_rejections():
             break
         x += 1
     assert O.g2_validate_uncompressed(g2_raw(((x, 0), y))) == O.INVALID_GROUP_POINT
+
+
+def _rand_twist_point(rng):
+    while True:
+        x = (rng.randrange(P.Q), rng.randrange(P.Q))
+        y2 = P.f2_add(P.f2_mul(P.f2_mul(x, x), x), P.B2)
+        y = P.f2_sqrt(y2)
+        if y is not None and P.f2_mul(y, y) == y2:
+            return (x, y)
+
+
+def _is_prime(n):  # deterministic enough: 24 Miller-Rabin bases
+    if n < 2:
+        return False
+    for p in (2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37):
+        if n % p == 0:
+            return n == p
+    d, s = n - 1, 0
+    while d % 2 == 0:
+        d, s = d // 2, s + 1
+    for a in (2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37, 41, 43, 47, 53, 59, 61, 67, 71, 73, 79, 83, 89):
+        x = pow(a, d, n)
+        if x in (1, n - 1):
+            continue
+        for _ in range(s - 1):
+            x = x * x % n
+            if x == n - 1:
+                break
+        else:
+            return False
+    return True
+
+
+def test_g2_subgroup_psi_criterion():
+    """The engine's r-torsion test (one 63-bit scalar multiplication and the psi endomorphism, csrc/items.cuh) decides
+    exactly what [r]P == infinity decides (AffineG2::new; SURVEY.md Appendix A).  E'(Fq2) has order r * h2 with h2 squarefree,
+    so it is the direct sum of its prime-order parts, psi acts on each part as a scalar, and the criterion's polynomial in
+    psi is zero on the r part (the generator passes) -- it is exact iff it is non-zero on each of the four other parts,
+    which one point of each prime order shows."""
+    rng = random.Random(5)
+    h2 = 2 * P.Q - P.R
+    fs = P.TWIST_COFACTOR_FACTORS
+    prod = 1
+    for f in fs:
+        assert _is_prime(f)
+        prod *= f
+    assert prod == h2 and len(set(fs)) == len(fs) and h2 % P.R != 0
+    n_twist = P.R * h2
+    assert P.g2_mul(_rand_twist_point(rng), n_twist) is None          # the group order of the twist
+    assert P.g2_psi(P.G2_GEN) == P.g2_mul(P.G2_GEN, P.Q % P.R)        # psi has eigenvalue q on G2
+    assert P.g2_in_subgroup_psi(P.G2_GEN) and P.g2_in_subgroup_psi(P.g2_mul(P.G2_GEN, rng.randrange(1, P.R)))
+    for f in fs:
+        s = None
+        while s is None:
+            s = P.g2_mul(_rand_twist_point(rng), n_twist // f)
+        assert P.g2_mul(s, f) is None                                 # order exactly f (prime)
+        assert not P.g2_in_subgroup_psi(s) and not P.g2_in_subgroup(s)
+        mixed = P.g2_add(s, P.g2_mul(P.G2_GEN, rng.randrange(1, P.R)))
+        assert not P.g2_in_subgroup_psi(mixed) and not P.g2_in_subgroup(mixed)
+    for _ in range(3):                                                # and a few random points, both ways
+        t = _rand_twist_point(rng)
+        assert P.g2_in_subgroup_psi(t) == P.g2_in_subgroup(t) is False
+        c = P.g2_mul(t, h2)
+        assert P.g2_in_subgroup_psi(c) == P.g2_in_subgroup(c) is True
