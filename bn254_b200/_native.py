@@ -12,6 +12,7 @@ SYMBOLS = [
     "bn254_set_profiling", "bn254_phase_ms", "bn254_set_pairing_mode",
     "bn254_hash_to_g1_batch", "bn254_hash_to_g1_batch_dev", "bn254_hash_to_g1_var",
     "bn254_sign_batch", "bn254_sign_batch_dev", "bn254_verify_batch", "bn254_verify_batch_dev",
+    "bn254_verify_batch_rlc", "bn254_verify_batch_rlc_dev",
     "bn254_check_public_keys_batch", "bn254_pairing_check_batch",
     "bn254_g1_sum", "bn254_g2_sum", "bn254_g1_sum_dev", "bn254_g2_sum_dev",
     "bn254_derive_pk_g2_batch", "bn254_derive_pk_g1_batch", "bn254_g1_mul_batch", "bn254_g2_mul_batch",
@@ -61,6 +62,8 @@ def _ptr(x):
         return ctypes.cast((ctypes.c_char * len(x)).from_buffer(x), ctypes.c_void_p) if len(x) else ctypes.c_void_p(0)
     if isinstance(x, ctypes.Array):
         return ctypes.cast(x, ctypes.c_void_p)
+    if isinstance(x, ctypes._SimpleCData):  # an out-parameter such as c_int
+        return ctypes.cast(ctypes.pointer(x), ctypes.c_void_p)
     if hasattr(x, "ctypes"):  # numpy array
         return ctypes.c_void_p(x.ctypes.data)
     if hasattr(x, "data_ptr"):  # torch tensor (host or device)

@@ -450,6 +450,22 @@ __global__ void k_coop_gather(const u4* __restrict__ fio, size_t L, size_t block
   out[b] = f;
 }
 
+// ---- randomised batch verification: per item c H(m) (in place) and c sig ; any item that cannot ride sets *bad
+__global__ void __launch_bounds__(BN_BLOCK) k_rlc_prepare(g1aff* __restrict__ H, const uint8_t* __restrict__ hstatus,
+                                                          const uint8_t* __restrict__ sigs, const uint8_t* __restrict__ pks,
+                                                          const uint8_t* __restrict__ coeffs16, size_t n, int check_g2,
+                                                          uint8_t* __restrict__ sig_c, unsigned* __restrict__ bad) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int st = hstatus[i];
+  if (!st) {
+    g1aff h = H[i], hs;
+    st = item_rlc_prepare(&hs, sig_c + 64 * i, &h, sigs + 64 * i, pks + 128 * i, coeffs16 + 16 * i, check_g2 != 0);
+    if (!st) H[i] = hs;
+  }
+  if (st) atomicOr(bad, 1u);
+}
+
 // ---- point aggregation: strided mixed additions per thread, then a shared-memory tree per block
 template <class F> struct pt_io;
 template <> struct pt_io<fq> {
@@ -1139,15 +1155,17 @@ static int sum_host_impl(bn254_ctx* ctx, const uint8_t* pts, const uint8_t* neg,
 }
 
 // Miller-product partial of (H(msg_i), pk_i), i < n  ->  f_be (384 bytes, device) ; status = first error or 0
-static int distinct_partial_dev(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, const uint8_t* pks, size_t n, uint8_t* f_be,
-                                uint8_t* status) {
-  size_t cap = n ? n : 1;
-  DALLOC(H, sizeof(g1aff) * cap);
-  DALLOC(hst, cap);
+struct dptr {  // a borrowed device pointer with the accessor of dbuf
+  void* p;
+  template <class T> T* as() { return (T*)p; }
+};
+// Miller-product partial of (P_i, pk_i), i < n, for G1 points already on the device (affine, Montgomery form; hst_p = their
+// per-item status)  ->  f_be (384 bytes, device) ; status = first error or 0
+static int distinct_partial_points_dev(bn254_ctx* ctx, g1aff* H_p, uint8_t* hst_p, const uint8_t* pks, size_t n, uint8_t* f_be,
+                                       uint8_t* status) {
+  dptr H{H_p}, hst{hst_p};
   DALLOC(err, 8);
   CK(cudaMemsetAsync(err.p, 0xff, 8, ctx->stream));
-  int rc = hash_dev(ctx, msgs, msg_len, nullptr, n, H.as<g1aff>(), hst.as<uint8_t>(), nullptr);
-  if (rc) return rc;
   if (ctx->pairing_mode != 1 && n > 0) {
     // cooperative multi-pairing: chunks of 2^20 pairs (26 GB of line sets), every block leaves one partial product
     const size_t CH = (size_t)1 << 20;
@@ -1184,8 +1202,98 @@ static int distinct_partial_dev(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_
   LAUNCH(k_fq12_prod_final, 1, BN_PROD_BLOCK, partial.as<fq12>(), (int)blocks, (fq12*)nullptr, f_be, err.as<unsigned long long>(), status);
   return 0;
 }
+// Miller-product partial of (H(msg_i), pk_i), i < n  ->  f_be (384 bytes, device) ; status = first error or 0
+static int distinct_partial_dev(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, const uint8_t* pks, size_t n, uint8_t* f_be,
+                                uint8_t* status) {
+  size_t cap = n ? n : 1;
+  DALLOC(H, sizeof(g1aff) * cap);
+  DALLOC(hst, cap);
+  int rc = hash_dev(ctx, msgs, msg_len, nullptr, n, H.as<g1aff>(), hst.as<uint8_t>(), nullptr);
+  if (rc) return rc;
+  return distinct_partial_points_dev(ctx, H.as<g1aff>(), hst.as<uint8_t>(), pks, n, f_be, status);
+}
+
+// ---- randomised batch verification (items.cuh item_rlc_prepare): fast path when every item rides, exact path otherwise
+static int verify_rlc_dev_impl(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, const uint8_t* sigs, const uint8_t* pks, size_t n,
+                               const uint8_t* coeffs16, int flags, uint8_t* status, int* took_fast_path) {
+  if (took_fast_path) *took_fast_path = 0;
+  if (n == 0) return 0;
+  DALLOC(H, sizeof(g1aff) * n);
+  DALLOC(hst, n);
+  DALLOC(sigc, 64 * n);
+  DALLOC(bad, 4);
+  DALLOC(fbe, 384);
+  DALLOC(agg, 64);
+  DALLOC(st2, 4);
+  CK(cudaMemsetAsync(bad.p, 0, 4, ctx->stream));
+  int rc = hash_dev(ctx, msgs, msg_len, nullptr, n, H.as<g1aff>(), hst.as<uint8_t>(), nullptr);
+  if (rc) return rc;
+  LAUNCH(k_rlc_prepare, grid_for(n), BN_BLOCK, H.as<g1aff>(), hst.as<uint8_t>(), sigs, pks, coeffs16, n, (flags & 1) ? 0 : 1,
+         sigc.as<uint8_t>(), bad.as<unsigned>());
+  unsigned h_bad = 0;
+  D2H(&h_bad, bad.p, 4);
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (!h_bad) {
+    // hst is all zero here (a hash error sets `bad`), H now holds c_i H(m_i)
+    rc = distinct_partial_points_dev(ctx, H.as<g1aff>(), hst.as<uint8_t>(), pks, n, fbe.as<uint8_t>(), st2.as<uint8_t>());
+    if (rc) return rc;
+    rc = sum_dev_impl<fq>(ctx, sigc.as<uint8_t>(), nullptr, n, agg.as<uint8_t>(), st2.as<uint8_t>() + 1);
+    if (rc) return rc;
+    LAUNCH(k_distinct_finish, 1, 32, fbe.as<uint8_t>(), 1, agg.as<uint8_t>(), ctx->d_lines, st2.as<uint8_t>() + 2);
+    uint8_t h_st[4] = {1, 1, 1, 1};
+    D2H(h_st, st2.p, 3);
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (h_st[0] == 0 && h_st[1] == 0 && h_st[2] == 0) {
+      CK(cudaMemsetAsync(status, 0, n, ctx->stream));
+      if (took_fast_path) *took_fast_path = 1;
+      return 0;
+    }
+  }
+  return verify_dev_impl(ctx, msgs, msg_len, sigs, pks, n, status);
+}
 
 extern "C" {
+
+int bn254_verify_batch_rlc_dev(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, const uint8_t* sigs, const uint8_t* pks, size_t n,
+                               const uint8_t* coeffs16, int flags, uint8_t* status, int* took_fast_path) {
+  ENTER();
+  ARGCHECK(n == 0 || (msgs && sigs && pks && coeffs16 && status));
+  return verify_rlc_dev_impl(ctx, msgs, msg_len, sigs, pks, n, coeffs16, flags, status, took_fast_path);
+}
+int bn254_verify_batch_rlc(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, const uint8_t* sigs, const uint8_t* pks, size_t n,
+                           const uint8_t* coeffs16, int flags, uint8_t* status, int* took_fast_path) {
+  ENTER();
+  ARGCHECK(n == 0 || (msgs && sigs && pks && status));
+  if (took_fast_path) *took_fast_path = 0;
+  if (n == 0) return 0;
+  std::vector<uint8_t> drawn;
+  if (!coeffs16) {  // the engine draws the coefficients itself (OS entropy): they must stay unknown to whoever made the signatures
+    drawn.resize(16 * n);
+    FILE* f = fopen("/dev/urandom", "rb");
+    size_t got = f ? fread(drawn.data(), 1, drawn.size(), f) : 0;
+    if (f) fclose(f);
+    if (got != drawn.size()) {
+      ctx->err = "bn254_verify_batch_rlc: cannot read /dev/urandom for the batch coefficients";
+      return BN254_E_ARG;
+    }
+    coeffs16 = drawn.data();
+  }
+  DALLOC(d_msgs, msg_len * n);
+  DALLOC(d_sigs, 64 * n);
+  DALLOC(d_pks, 128 * n);
+  DALLOC(d_c, 16 * n);
+  DALLOC(d_st, n);
+  if (msg_len) H2D(d_msgs.p, msgs, msg_len * n);
+  H2D(d_sigs.p, sigs, 64 * n);
+  H2D(d_pks.p, pks, 128 * n);
+  H2D(d_c.p, coeffs16, 16 * n);
+  int rc = verify_rlc_dev_impl(ctx, d_msgs.as<uint8_t>(), msg_len, d_sigs.as<uint8_t>(), d_pks.as<uint8_t>(), n, d_c.as<uint8_t>(), flags,
+                               d_st.as<uint8_t>(), took_fast_path);
+  if (rc) return rc;
+  D2H(status, d_st.p, n);
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
 
 int bn254_g1_mul_batch(bn254_ctx* ctx, const uint8_t* pts, const uint8_t* scalars, size_t n, uint8_t* out64, uint8_t* status) {
   return item_op_host<OP_G1_MUL>(ctx, pts, 64, scalars, 32, n, out64, 64, status);

@@ -161,7 +161,7 @@ BN_NOINLINE bool pt_to_affine(F* x, F* y, const jac<F>* p) {
 // scalar multiplication by a 256-bit integer k (8 plain limbs), 4-bit fixed windows, MSB first.
 // Uniform schedule: 4 doublings + one table addition per window (skipped only for a zero digit).
 template <class F>
-BN_NOINLINE void pt_mul(jac<F>* r, const jac<F>* p, const uint32_t* k) {
+BN_NOINLINE void pt_mul(jac<F>* r, const jac<F>* p, const uint32_t* k, int windows = 64) {
   jac<F> tab[16];
   pt_set_inf(&tab[0]);
   tab[1] = *p;
@@ -169,7 +169,7 @@ BN_NOINLINE void pt_mul(jac<F>* r, const jac<F>* p, const uint32_t* k) {
   for (int i = 3; i < 16; i++) pt_add(&tab[i], &tab[i - 1], p);
   jac<F> acc;
   pt_set_inf(&acc);
-  for (int w = 63; w >= 0; w--) {
+  for (int w = windows - 1; w >= 0; w--) {  // windows < 64: the caller knows that k < 16^windows
     for (int d = 0; d < 4; d++) pt_dbl(&acc, &acc);
     uint32_t nib = (k[w >> 3] >> ((w & 7) * 4)) & 15;
     if (nib) pt_add(&acc, &acc, &tab[nib]);

@@ -222,6 +222,36 @@ BN_FN int item_g2_validate(const uint8_t* raw) {
   return ST_OK;
 }
 
+// ---------------------------------------------------------------------------------------------- randomised batch verification
+// SURVEY.md 8(f) row 4 -- an ADDITIONAL entry point next to ECDSA::verify (/root/reference/src/ecdsa.rs:49-64), not a
+// replacement: n independent triples are accepted together iff
+//     prod_i e(c_i H(m_i), pk_i) * e(sum_i c_i sig_i, -G2) == 1        (c_i: secret random 128-bit coefficients)
+// which, for keys in G2, holds for all-valid batches and fails with probability 1 - 2^-128 otherwise.  This is one item's
+// share: hs = c H(m) (affine, Montgomery form) and c sig (raw bytes).  Returns 0 when the item can ride in the batch
+// (both points decode, pk is in the r-torsion unless the caller vouches for it); anything else sends the whole batch to
+// the exact per-item path, so the statuses a caller sees are always those of verify_batch.
+BN_FN int item_rlc_prepare(g1aff* hs, uint8_t* sig_c_raw, const g1aff* h, const uint8_t* sig_raw, const uint8_t* pk_raw,
+                           const uint8_t* c16_be, bool check_g2) {
+  g1j s, t;
+  g2j q;
+  int st = g1_from_raw(&s, sig_raw);
+  if (st) return st;
+  st = g2_from_raw(&q, pk_raw);
+  if (st) return st;
+  if (check_g2 && !pt_is_inf(&q) && !g2_in_subgroup(&q)) return ST_INVALID_GROUP_POINT;
+  uint32_t k[8];
+  for (int i = 0; i < 4; i++)
+    k[i] = ((uint32_t)c16_be[12 - 4 * i] << 24) | ((uint32_t)c16_be[13 - 4 * i] << 16) | ((uint32_t)c16_be[14 - 4 * i] << 8) | c16_be[15 - 4 * i];
+  for (int i = 4; i < 8; i++) k[i] = 0;
+  if ((k[0] | k[1] | k[2] | k[3]) == 0) k[0] = 1;  // a zero coefficient would drop the item from the check
+  pt_set_affine(&t, h->x, h->y);
+  pt_mul(&t, &t, k, 32);
+  pt_to_affine(&hs->x, &hs->y, &t);  // never infinity: H(m) has prime order r > c
+  pt_mul(&s, &s, k, 32);
+  g1_to_raw(sig_c_raw, &s);
+  return ST_OK;
+}
+
 // (im, re) compared as the 512-bit integer im*q + re (to_u512, /root/reference/src/utils.rs:40-45): lexicographic
 BN_FN bool fq2_u512_gt(const fq2& a, const fq2& b) {
   fq ai = fq_from_mont(a.c1), bi = fq_from_mont(b.c1);

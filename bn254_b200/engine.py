@@ -49,6 +49,18 @@ def sign_batch(msgs, msg_len, sks, ctx=None):
     return o.raw[:64 * n], st.raw[:n]
 
 
+def verify_batch_rlc(msgs, msg_len, sigs, pks, coeffs16=None, pks_in_g2=False, ctx=None):
+    """Randomised batch form of verify_batch (bn254_verify_batch_rlc): -> (statuses, took_fast_path).  The statuses are
+    verify_batch's; `coeffs16` (16 secret random bytes per item) defaults to the engine drawing them from /dev/urandom."""
+    import ctypes
+    ctx = ctx or context()
+    n = _n(sigs, 64)
+    assert _n(pks, 128) == n and (coeffs16 is None or len(coeffs16) == 16 * n)
+    st, fast = out(n), ctypes.c_int(0)
+    ctx.call("bn254_verify_batch_rlc", msgs, S(msg_len), sigs, pks, S(n), coeffs16, I(1 if pks_in_g2 else 0), st, fast)
+    return st.raw[:n], bool(fast.value)
+
+
 def verify_batch(msgs, msg_len, sigs, pks, ctx=None):
     ctx = ctx or context()
     n = _n(sigs, 64)

@@ -89,6 +89,18 @@ int bn254_sign_batch_dev(bn254_ctx*, const uint8_t* msgs, size_t msg_len, const 
 int bn254_verify_batch(bn254_ctx*, const uint8_t* msgs, size_t msg_len, const uint8_t* sigs, const uint8_t* pks, size_t n, uint8_t* status);
 int bn254_verify_batch_dev(bn254_ctx*, const uint8_t* msgs, size_t msg_len, const uint8_t* sigs, const uint8_t* pks, size_t n, uint8_t* status);
 
+/* Randomised batch form of ECDSA::verify -- an ADDITIONAL entry point, never used by verify_batch: the n
+ * triples are accepted together iff  prod_i e(c_i H(msg_i), pk_i) * e(sum_i c_i sig_i, -G2) == 1  for 128-bit coefficients
+ * c_i (coeffs16: n x 16 bytes big-endian, secret from whoever produced the signatures; NULL in the host-buffer form = drawn
+ * from /dev/urandom).  One shared final exponentiation instead of n.  If every item decodes, every pk is in G2 and the
+ * combined check passes, all statuses are 0 (what verify_batch returns, up to a 2^-128 false-accept probability) and
+ * *took_fast_path = 1; in every other case the exact per-item path runs and status[] is exactly verify_batch's.
+ * flags bit 0: the caller vouches that every pk is in the r-torsion (e.g. it came from from_compressed) -- skips that test. */
+int bn254_verify_batch_rlc(bn254_ctx*, const uint8_t* msgs, size_t msg_len, const uint8_t* sigs, const uint8_t* pks, size_t n,
+                           const uint8_t* coeffs16, int flags, uint8_t* status, int* took_fast_path);
+int bn254_verify_batch_rlc_dev(bn254_ctx*, const uint8_t* msgs, size_t msg_len, const uint8_t* sigs, const uint8_t* pks, size_t n,
+                               const uint8_t* coeffs16, int flags, uint8_t* status, int* took_fast_path);
+
 /* check_public_keys (/root/reference/src/ecdsa.rs:78-93): e(G1, pk_g2_i) * e(pk_g1_i, -G2) == 1 */
 int bn254_check_public_keys_batch(bn254_ctx*, const uint8_t* pk_g2, const uint8_t* pk_g1, size_t n, uint8_t* status);
 

@@ -15,7 +15,7 @@ import torch
 
 import synth
 from bn254_b200 import engine as E
-from bn254_b200._native import S
+from bn254_b200._native import I, S
 
 
 def timed(ctx, fn, reps=3):
@@ -64,6 +64,14 @@ def main():
     agg, _ = E.g1_sum(sigs[:64 * m5], ctx=ctx)
     v = E.finish_distinct(bytes(d_f.cpu().numpy().tobytes()), agg, ctx=ctx)
     print(json.dumps({"config": "5: distinct-message aggregate verify (Miller partial of %d pairs + shared final exp)" % m5, "pairs_per_sec": m5 / dt, "ms": dt * 1e3, "status": v}))
+    # randomised batch verification (additional entry point): all-valid batch, device-resident inputs
+    import ctypes
+    d_c = dev(synth.rand_bytes(77, 16 * n))
+    fast = ctypes.c_int(0)
+    for flags, label in ((0, "with the r-torsion test of every key"), (1, "keys vouched for by the caller")):
+        dt = timed(ctx, lambda: ctx.call("bn254_verify_batch_rlc_dev", d_msgs, S(32), d_sigs, d_pks, S(n), d_c, I(flags), d_st, fast), reps=2)
+        assert fast.value == 1 and not d_st.any().item()
+        print(json.dumps({"config": "randomised batch verify (one shared final exponentiation), " + label, "n": n, "verifies_per_sec": n / dt, "ms": dt * 1e3}))
     m6 = min(n, 1 << 18)
     comp, st = E.g2_compress_batch(pks[:128 * m6], ctx=ctx)
     raw, st = E.g2_decompress_batch(comp, ctx=ctx)  # warm

@@ -167,6 +167,18 @@ API int hs_layer_op(int op, const uint8_t* in, int n_in, uint8_t* out, int n_out
   return 0;
 }
 
+// randomised batch verification, one item's share: c * H(msg) (raw) and c * sig (raw) ; returns the ride / no-ride status
+API int hs_rlc_prepare(const uint8_t* msg, size_t len, const uint8_t* sig, const uint8_t* pk, const uint8_t* c16, int check_g2,
+                       uint8_t* hs_out, uint8_t* sigc_out) {
+  g1aff h, hs;
+  int st = hash_to_g1(&h.x, &h.y, msg, len, nullptr);
+  if (st) return st;
+  st = item_rlc_prepare(&hs, sigc_out, &h, sig, pk, c16, check_g2 != 0);
+  if (st) return st;
+  fq_to_be(hs_out, hs.x); fq_to_be(hs_out + 32, hs.y);
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------- cooperative machine
 // The six warps of a block are simulated one after the other, phase by phase, for lane 0 of one block.
 #include "../../bn254_b200/csrc/coop_lines.cuh"

@@ -527,3 +527,58 @@ def test_distinct_partial_modes_bit_identical(E):
         assert E.miller_partial_distinct(msgs, 32, bytes(bad), ctx=ctx)[1] == O.INVALID_GROUP_POINT
     ctx.call("bn254_set_pairing_mode", I(0))
     assert E.miller_partial_distinct(b"", 32, b"", ctx=ctx)[0] == be(1) + bytes(352)
+
+
+def test_verify_batch_rlc(E):
+    """Randomised batch verification: the fast path is taken exactly when every
+    item is valid, and the statuses are always those of verify_batch / the oracle -- including a pair of forged signatures
+    whose errors cancel in an unrandomised aggregate check."""
+    import edge_points
+    n = 600
+    msgs, sks, sigs, pks = _signed_set(E, n, seed=57)
+    coeffs = synth.rand_bytes(1234, 16 * n)
+    st, fast = E.verify_batch_rlc(msgs, 32, sigs, pks, coeffs)
+    assert fast and st == bytes(n)
+    st, fast = E.verify_batch_rlc(msgs, 32, sigs, pks)                      # coefficients drawn by the engine
+    assert fast and st == bytes(n)
+    st, fast = E.verify_batch_rlc(msgs, 32, sigs, pks, coeffs, pks_in_g2=True)
+    assert fast and st == bytes(n)
+    st, fast = E.verify_batch_rlc(msgs, 32, sigs, pks, bytes(16 * n))       # zero coefficients count as one
+    assert fast and st == bytes(n)
+    for size in (1, 7, 255, 257):                                           # around the 256-pair group of the multi-pairing machine
+        st, fast = E.verify_batch_rlc(msgs[:32 * size], 32, sigs[:64 * size], pks[:128 * size], coeffs[:16 * size])
+        assert fast and st == bytes(size), size
+    # infinite signature + infinite key: both pairs are skipped, the item is accepted (bn::pairing_batch semantics)
+    s2, p2 = bytearray(sigs), bytearray(pks)
+    s2[64 * 5:64 * 6] = bytes(64)
+    p2[128 * 5:128 * 6] = bytes(128)
+    st, fast = E.verify_batch_rlc(msgs, 32, bytes(s2), bytes(p2), coeffs)
+    assert fast and st == bytes(n) == E.verify_batch(msgs, 32, bytes(s2), bytes(p2))
+    # one wrong signature: the combined check fails, the exact path decides
+    s3 = bytearray(sigs)
+    s3[64 * 77:64 * 78] = O.g1_neg(sigs[64 * 77:64 * 78])[1]
+    st, fast = E.verify_batch_rlc(msgs, 32, bytes(s3), pks, coeffs)
+    want = O.verify_batch(msgs, 32, bytes(s3), pks, n, NTHREADS)
+    assert not fast and st == want and st[77] == O.VERIFICATION_FAILED and sum(st) == O.VERIFICATION_FAILED
+    # cancelling forgeries: sig_a + D and sig_b - D leave the plain sum of signatures unchanged
+    d = O.derive_pk_g1(be(4242))[1]
+    s4 = bytearray(sigs)
+    s4[64 * 10:64 * 11] = O.g1_add(sigs[64 * 10:64 * 11], d)[1]
+    s4[64 * 20:64 * 21] = O.g1_add(sigs[64 * 20:64 * 21], O.g1_neg(d)[1])[1]
+    st, fast = E.verify_batch_rlc(msgs, 32, bytes(s4), pks, coeffs)
+    want = O.verify_batch(msgs, 32, bytes(s4), pks, n, NTHREADS)
+    assert not fast and st == want and st[10] == st[20] == O.VERIFICATION_FAILED
+    ones = (bytes(15) + b"\x01") * n   # a caller that does not randomise is fooled: this is why the coefficients must be secret and random
+    st, fast = E.verify_batch_rlc(msgs, 32, bytes(s4), pks, ones)
+    assert fast and st == bytes(n)
+    # undecodable items and a key outside G2 never ride
+    s5 = bytearray(sigs)
+    s5[64 * 3 + 63] ^= 1
+    st, fast = E.verify_batch_rlc(msgs, 32, bytes(s5), pks, coeffs)
+    assert not fast and st == O.verify_batch(msgs, 32, bytes(s5), pks, n, NTHREADS) and st[3] != 0
+    outside = [pt for pt, inside in edge_points.subgroup_edge_points() if not inside][1]
+    p6 = bytearray(pks)
+    p6[128 * 9:128 * 10] = outside
+    st, fast = E.verify_batch_rlc(msgs, 32, sigs, bytes(p6), coeffs)
+    assert not fast and st == O.verify_batch(msgs, 32, sigs, bytes(p6), n, NTHREADS) == E.verify_batch(msgs, 32, sigs, bytes(p6))
+    assert E.verify_batch_rlc(b"", 32, b"", b"") == (b"", False)

@@ -313,3 +313,25 @@ def test_fixed_base_tables(hs):
         hs.hs_derive_pk_g1_comb(sk, o1)
         hs.hs_derive_pk_g2_comb(sk, o2)
         assert o1.raw == O.derive_pk_g1(sk)[1] and o2.raw == O.derive_pk_g2(sk)[1], sk.hex()
+
+
+def test_rlc_prepare_item(hs):
+    """One item's share of the randomised batch check: c * H(m) and c * sig for a 128-bit coefficient (zero is replaced by one),
+    and the conditions under which an item may not ride in the batch (bad encodings, a key outside G2)."""
+    import edge_points
+    rng = random.Random(23)
+    sk = be(rng.randrange(1, R))
+    msg = rng.randbytes(32)
+    sig, pk, h = O.sign(msg, sk)[1], O.derive_pk_g2(sk)[1], O.hash_to_g1(msg)[1]
+    for c in (rng.randrange(1, 1 << 128), 1, (1 << 128) - 1, 0, 1 << 127, 0xf):
+        hs_out, sc_out = buf(64), buf(64)
+        assert hs.hs_rlc_prepare(msg, len(msg), sig, pk, be(c, 16), 1, hs_out, sc_out) == 0
+        k = be(c or 1)
+        assert hs_out.raw == O.g1_mul(h, k)[1] and sc_out.raw == O.g1_mul(sig, k)[1]
+    hs_out, sc_out = buf(64), buf(64)
+    assert hs.hs_rlc_prepare(msg, len(msg), bytes(64), bytes(128), be(5, 16), 1, hs_out, sc_out) == 0 and sc_out.raw == bytes(64)
+    assert hs.hs_rlc_prepare(msg, len(msg), be(1) + be(3), pk, be(5, 16), 1, hs_out, sc_out) == O.INVALID_GROUP_POINT
+    assert hs.hs_rlc_prepare(msg, len(msg), sig, pk[:127] + bytes([pk[127] ^ 1]), be(5, 16), 1, hs_out, sc_out) == O.INVALID_GROUP_POINT
+    outside = [pt for pt, inside in edge_points.subgroup_edge_points() if not inside][0]
+    assert hs.hs_rlc_prepare(msg, len(msg), sig, outside, be(5, 16), 1, hs_out, sc_out) == O.INVALID_GROUP_POINT
+    assert hs.hs_rlc_prepare(msg, len(msg), sig, outside, be(5, 16), 0, hs_out, sc_out) == 0   # the caller vouched for the key
