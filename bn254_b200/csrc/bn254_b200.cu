@@ -318,6 +318,9 @@ __global__ void __launch_bounds__(BN_BLOCK, BN_LINES_MINB) k_verify_lines(const 
 #ifndef BN_COOP_MINB
 #define BN_COOP_MINB 4
 #endif
+#ifndef BN_COOP_STAGGER
+#define BN_COOP_STAGGER 0
+#endif
 #ifndef BN_COOP_DEFAULT_W
 #define BN_COOP_DEFAULT_W false
 #endif
@@ -325,8 +328,17 @@ __global__ void __launch_bounds__(BN_BLOCK, BN_LINES_MINB) k_verify_lines(const 
 // 3 final exponentiation of fio (+ verdict), 4 multi-pairing: COOP_MULTI_K pairs per lane, block product -> fio
 __global__ void __launch_bounds__(COOP_THREADS, BN_COOP_MINB) k_coop_run(int which, size_t n, size_t n_pad, const u4* __restrict__ lines,
                                                                          u4* __restrict__ gslots, u4* __restrict__ fio,
-                                                                         uint8_t* __restrict__ status) {
+                                                                         uint8_t* __restrict__ status, unsigned stagger, unsigned sms) {
   extern __shared__ u4 coop_sm[];
+  // Blocks that share an SM run the same program at the same speed: started together they stay in lockstep, so their
+  // multiply-free stretches (commit, barriers) coincide and the multiplier pipe idles for all of them at once.  The k-th
+  // co-resident block of the first wave therefore starts k * stagger cycles late (blocks of later waves inherit the offsets).
+  if (stagger) {
+    const unsigned slot = (blockIdx.x / sms) % BN_COOP_MINB;
+    const long long t0 = clock64();
+    while (clock64() - t0 < (long long)slot * stagger) {
+    }
+  }
   coop_ctx c;
   c.k = threadIdx.x >> 5;
   c.lane = threadIdx.x & 31;
@@ -632,6 +644,7 @@ struct bn254_ctx {
   // 0: cooperative machine (coop.cuh) in its default layout, 1: one thread per item (pairing.cuh),
   // 2: cooperative, block layout (six warps per 32 items), 3: cooperative, warp-local layout (six lanes per item)
   int pairing_mode = 0;
+  unsigned coop_stagger = BN_COOP_STAGGER;  // start offset between co-resident blocks of k_coop_run, SM cycles
   bool coop_w = BN_COOP_DEFAULT_W;  // layout mode 0 uses for verify (BN254_COOP_W=0/1 in the environment overrides)
   std::string err;
   // optional per-phase timing of the verify pipeline (bn254_set_profiling): events recorded on `stream`
@@ -683,6 +696,7 @@ int bn254_ctx_create(int device, bn254_ctx** out) {
   bn254_ctx* ctx = new bn254_ctx();
   ctx->device = device;
   if (const char* w = getenv("BN254_COOP_W")) ctx->coop_w = w[0] == '1';
+  if (const char* w = getenv("BN254_COOP_STAGGER")) ctx->coop_stagger = (unsigned)atoi(w);  // tuning knob (cycles)
   auto fail = [&](const char* what, cudaError_t ee) {
     g_create_err = std::string(what) + ": " + cudaGetErrorString(ee);
     delete ctx;
@@ -916,7 +930,7 @@ static int verify_dev_impl(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, 
             0, m, m_pad, LN.as<u4>(), GS.as<u4>(), (u4*)nullptr, status + off);
       else
         k_coop_run<<<(unsigned)(m_pad / COOP_LANES), COOP_THREADS, COOP_SMEM_BYTES, ctx->stream>>>(0, m, m_pad, LN.as<u4>(), GS.as<u4>(),
-                                                                                                    (u4*)nullptr, status + off);
+                                                                                                    (u4*)nullptr, status + off, ctx->coop_stagger, (unsigned)ctx->sm_count);
       ctx->launches++;
       CK(cudaGetLastError());
       CK(mark());
@@ -1183,7 +1197,7 @@ static int distinct_partial_points_dev(bn254_ctx* ctx, g1aff* H_p, uint8_t* hst_
       size_t blocks = (m + per_block - 1) / per_block, L = blocks * COOP_LANES;
       LAUNCH(k_pair_lines, grid_for(L * COOP_MULTI_K), BN_BLOCK, H.as<g1aff>() + off, hst.as<uint8_t>() + off, pks + 128 * off, m, L, LN.as<u4>(),
              err.as<unsigned long long>(), off);
-      k_coop_run<<<(unsigned)blocks, COOP_THREADS, COOP_SMEM_BYTES, ctx->stream>>>(4, L, L, LN.as<u4>(), (u4*)nullptr, FIO.as<u4>(), (uint8_t*)nullptr);
+      k_coop_run<<<(unsigned)blocks, COOP_THREADS, COOP_SMEM_BYTES, ctx->stream>>>(4, L, L, LN.as<u4>(), (u4*)nullptr, FIO.as<u4>(), (uint8_t*)nullptr, ctx->coop_stagger, (unsigned)ctx->sm_count);
       ctx->launches++;
       CK(cudaGetLastError());
       LAUNCH(k_coop_gather, grid_for(blocks), BN_BLOCK, FIO.as<u4>(), L, blocks, partial.as<fq12>() + done_blocks);

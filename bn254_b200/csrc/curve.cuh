@@ -177,6 +177,92 @@ BN_NOINLINE void pt_mul(jac<F>* r, const jac<F>* p, const uint32_t* k, int windo
   *r = acc;
 }
 
+// ---- GLV scalar multiplication in G1 (signing, /root/reference/src/ecdsa.rs:28-31, multiplies the per-message hash point,
+// so no fixed-base table applies).  phi(x, y) = (beta x, y) equals [lambda](x, y) on G1 (beta, lambda: cube roots of unity
+// in Fq, Fr), and every k < r splits as k = k1 + k2 lambda (mod r) with |k1|, |k2| < 2^128 (constants.cuh K_GLV_*, derived
+// and bounded in scripts/gen_constants.py): [k]P = [k1]P + [k2]phi(P) costs 128 doublings instead of 256.  The group
+// element is the same, so the serialised signature is bit-identical to the double-and-add result.
+// out (n limbs) = low n limbs of a (na limbs) * b (nb limbs)
+BN_FN void limbs_mul(uint32_t* out, int n, const uint32_t* a, int na, const uint32_t* b, int nb) {
+  for (int i = 0; i < n; i++) out[i] = 0;
+  for (int i = 0; i < na; i++) {
+    uint64_t c = 0;
+    for (int j = 0; j < nb && i + j < n; j++) {
+      c += (uint64_t)a[i] * b[j] + out[i + j];
+      out[i + j] = (uint32_t)c;
+      c >>= 32;
+    }
+    for (int t = i + nb; t < n && c; t++) {
+      c += out[t];
+      out[t] = (uint32_t)c;
+      c >>= 32;
+    }
+  }
+}
+// k (8 limbs, k < r) -> magnitudes (4 limbs each) and signs of k1, k2
+BN_FN void glv_decompose(uint32_t* k1, bool* neg1, uint32_t* k2, bool* neg2, const uint32_t* k) {
+  uint32_t t[13], c1[3], c2[5], u[8], v[8], w[8];
+  limbs_mul(t, 11, k, 8, K_GLV_G1, 3);  // c1 = (k g1) >> 256
+  for (int i = 0; i < 3; i++) c1[i] = t[8 + i];
+  limbs_mul(t, 13, k, 8, K_GLV_G2, 5);  // c2 = (k g2) >> 256
+  for (int i = 0; i < 5; i++) c2[i] = t[8 + i];
+  // k1 = k - c1 a1 - c2 a2 and k2 = c1 |b1| - c2 b2, two's complement mod 2^256 (the true values are below 2^128 in size)
+  limbs_mul(u, 8, c1, 3, K_GLV_A1, 2);
+  limbs_mul(v, 8, c2, 5, K_GLV_A2, 4);
+  u256_sub(w, k, u);
+  u256_sub(w, w, v);
+  *neg1 = (w[7] >> 31) != 0;
+  if (*neg1) {
+    for (int i = 0; i < 8; i++) u[i] = 0;
+    u256_sub(w, u, w);
+  }
+  for (int i = 0; i < 4; i++) k1[i] = w[i];
+  limbs_mul(u, 8, c1, 3, K_GLV_B1N, 4);
+  limbs_mul(v, 8, c2, 5, K_GLV_B2, 2);
+  u256_sub(w, u, v);
+  *neg2 = (w[7] >> 31) != 0;
+  if (*neg2) {
+    for (int i = 0; i < 8; i++) u[i] = 0;
+    u256_sub(w, u, w);
+  }
+  for (int i = 0; i < 4; i++) k2[i] = w[i];
+}
+// [k]p for k < r (8 plain limbs) is g1_mul_pair over the decomposition: 32 windows of 4 bits, one table of multiples of p
+// shared by both halves
+// r = [+-k1]p + [+-k2]phi(p), k1 and k2 below 16^windows
+BN_NOINLINE void g1_mul_pair(jac<fq>* r, const jac<fq>* p, const uint32_t* k1, bool n1, const uint32_t* k2, bool n2, int windows) {
+  jac<fq> tab[16];
+  pt_set_inf(&tab[0]);
+  tab[1] = *p;
+  pt_dbl(&tab[2], p);
+  for (int i = 3; i < 16; i++) pt_add(&tab[i], &tab[i - 1], p);
+  const fq beta = fq_from_limbs(K_GLV_BETA);
+  jac<fq> acc, t;
+  pt_set_inf(&acc);
+  for (int w = windows - 1; w >= 0; w--) {
+    for (int d = 0; d < 4; d++) pt_dbl(&acc, &acc);
+    uint32_t d1 = (k1[w >> 3] >> ((w & 7) * 4)) & 15, d2 = (k2[w >> 3] >> ((w & 7) * 4)) & 15;
+    if (d1) {
+      t = tab[d1];
+      if (n1) t.y = fq_neg(t.y);
+      pt_add(&acc, &acc, &t);
+    }
+    if (d2) {
+      t = tab[d2];
+      t.x = fq_mul(t.x, beta);  // phi on Jacobian coordinates: (beta X, Y, Z)
+      if (n2) t.y = fq_neg(t.y);
+      pt_add(&acc, &acc, &t);
+    }
+  }
+  *r = acc;
+}
+BN_FN void g1_mul_glv(jac<fq>* r, const jac<fq>* p, const uint32_t* k) {
+  uint32_t k1[4], k2[4];
+  bool n1, n2;
+  glv_decompose(k1, &n1, k2, &n2, k);
+  g1_mul_pair(r, p, k1, n1, k2, n2, 32);
+}
+
 // ---- fixed-base scalar multiplication (key derivation, /root/reference/src/types.rs:85-87,155-157): a table of
 // d * 16^w * G (w = 0..63, d = 1..15, affine) turns G * k into at most 64 mixed additions and no doubling.
 template <class F>

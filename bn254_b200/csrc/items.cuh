@@ -32,7 +32,7 @@ BN_FN void item_sign(uint8_t* sig_out, const g1aff* h, const uint8_t* sk_be) {
   fr_reduce(k, sk_be);
   g1j p, s;
   pt_set_affine(&p, h->x, h->y);
-  pt_mul(&s, &p, k);
+  g1_mul_glv(&s, &p, k);
   g1_to_raw(sig_out, &s);
 }
 // generic point * 256-bit scalar (no reduction; bn256.json `mul` vectors use scalars >= r)
@@ -44,8 +44,8 @@ BN_FN int item_g1_mul(uint8_t* out, const uint8_t* pt, const uint8_t* k_be) {
     return st;
   }
   uint32_t k[8];
-  u256_from_be(k, k_be);
-  pt_mul(&s, &p, k);
+  fr_reduce(k, k_be);  // every point of the curve has order r (cofactor 1), so [k]P = [k mod r]P
+  g1_mul_glv(&s, &p, k);
   g1_to_raw(out, &s);
   return ST_OK;
 }
@@ -239,15 +239,17 @@ BN_FN int item_rlc_prepare(g1aff* hs, uint8_t* sig_c_raw, const g1aff* h, const 
   st = g2_from_raw(&q, pk_raw);
   if (st) return st;
   if (check_g2 && !pt_is_inf(&q) && !g2_in_subgroup(&q)) return ST_INVALID_GROUP_POINT;
-  uint32_t k[8];
+  // The 16 coefficient bytes are read as two 64-bit halves and the item's coefficient is c = c_lo + c_hi * lambda (mod r):
+  // still 2^128 equally likely values (the map is injective: |c_lo|, |c_hi| < 2^64 is far inside the GLV lattice's
+  // fundamental cell), and [c]P = [c_lo]P + [c_hi]phi(P) needs 64 doublings instead of 128.
+  uint32_t k[4];
   for (int i = 0; i < 4; i++)
     k[i] = ((uint32_t)c16_be[12 - 4 * i] << 24) | ((uint32_t)c16_be[13 - 4 * i] << 16) | ((uint32_t)c16_be[14 - 4 * i] << 8) | c16_be[15 - 4 * i];
-  for (int i = 4; i < 8; i++) k[i] = 0;
   if ((k[0] | k[1] | k[2] | k[3]) == 0) k[0] = 1;  // a zero coefficient would drop the item from the check
   pt_set_affine(&t, h->x, h->y);
-  pt_mul(&t, &t, k, 32);
-  pt_to_affine(&hs->x, &hs->y, &t);  // never infinity: H(m) has prime order r > c
-  pt_mul(&s, &s, k, 32);
+  g1_mul_pair(&t, &t, k, false, k + 2, false, 16);
+  pt_to_affine(&hs->x, &hs->y, &t);  // never infinity: c != 0 mod r and H(m) has prime order r
+  g1_mul_pair(&s, &s, k, false, k + 2, false, 16);
   g1_to_raw(sig_c_raw, &s);
   return ST_OK;
 }

@@ -91,8 +91,9 @@ int bn254_verify_batch_dev(bn254_ctx*, const uint8_t* msgs, size_t msg_len, cons
 
 /* Randomised batch form of ECDSA::verify -- an ADDITIONAL entry point, never used by verify_batch: the n
  * triples are accepted together iff  prod_i e(c_i H(msg_i), pk_i) * e(sum_i c_i sig_i, -G2) == 1  for 128-bit coefficients
- * c_i (coeffs16: n x 16 bytes big-endian, secret from whoever produced the signatures; NULL in the host-buffer form = drawn
- * from /dev/urandom).  One shared final exponentiation instead of n.  If every item decodes, every pk is in G2 and the
+ * c_i (coeffs16: n x 16 bytes, secret from whoever produced the signatures; NULL in the host-buffer form = drawn from
+ * /dev/urandom; the bytes are read as two 64-bit halves and c_i = lo + hi * lambda mod r, lambda the GLV eigenvalue, which
+ * keeps 2^128 distinct coefficients and halves the scalar multiplications).  One shared final exponentiation instead of n.  If every item decodes, every pk is in G2 and the
  * combined check passes, all statuses are 0 (what verify_batch returns, up to a 2^-128 false-accept probability) and
  * *took_fast_path = 1; in every other case the exact per-item path runs and status[] is exactly verify_batch's.
  * flags bit 0: the caller vouches that every pk is in the r-torsion (e.g. it came from from_compressed) -- skips that test. */

@@ -326,7 +326,9 @@ def test_rlc_prepare_item(hs):
     for c in (rng.randrange(1, 1 << 128), 1, (1 << 128) - 1, 0, 1 << 127, 0xf):
         hs_out, sc_out = buf(64), buf(64)
         assert hs.hs_rlc_prepare(msg, len(msg), sig, pk, be(c, 16), 1, hs_out, sc_out) == 0
-        k = be(c or 1)
+        c = c or 1
+        lam = 0xb3c4d79d41a917585bfc41088d8daaa78b17ea66b99c90dd   # the coefficient is lo + hi * lambda (GLV-shaped, one 64-bit ladder)
+        k = be(((c & ((1 << 64) - 1)) + (c >> 64) * lam) % R)
         assert hs_out.raw == O.g1_mul(h, k)[1] and sc_out.raw == O.g1_mul(sig, k)[1]
     hs_out, sc_out = buf(64), buf(64)
     assert hs.hs_rlc_prepare(msg, len(msg), bytes(64), bytes(128), be(5, 16), 1, hs_out, sc_out) == 0 and sc_out.raw == bytes(64)
@@ -335,3 +337,19 @@ def test_rlc_prepare_item(hs):
     outside = [pt for pt, inside in edge_points.subgroup_edge_points() if not inside][0]
     assert hs.hs_rlc_prepare(msg, len(msg), sig, outside, be(5, 16), 1, hs_out, sc_out) == O.INVALID_GROUP_POINT
     assert hs.hs_rlc_prepare(msg, len(msg), sig, outside, be(5, 16), 0, hs_out, sc_out) == 0   # the caller vouched for the key
+
+
+def test_sign_glv_edge_scalars(hs):
+    """Signing multiplies the hash point by k = k1 + k2 * lambda (GLV, csrc/curve.cuh g1_mul_glv): same group element, hence the
+    same bytes as the oracle's double-and-add, for the scalars where the decomposition changes sign or hits its bounds."""
+    lam = 0xb3c4d79d41a917585bfc41088d8daaa78b17ea66b99c90dd
+    a1, a2 = 0x89d3256894d213e3, 0x6f4d8248eeb859fd0be4e1541221250b
+    rng = random.Random(29)
+    ks = [0, 1, 2, 15, 16, R - 1, R - 2, R, R + 1, (1 << 256) - 1, lam, lam - 1, lam + 1, R - lam, a1, a2, a1 * a2 % R, (1 << 128) - 1, 1 << 128,
+          (1 << 253), (1 << 254) - 1, R // 2, R // 2 + 1, R // 3]
+    ks += [rng.randrange(1 << 256) for _ in range(40)]
+    for k in ks:
+        msg = rng.randbytes(rng.randrange(0, 70))
+        out = buf(64)
+        assert hs.hs_sign(msg, len(msg), be(k), out) == 0
+        assert out.raw == O.sign(msg, be(k))[1], hex(k)
