@@ -167,6 +167,16 @@ API int hs_layer_op(int op, const uint8_t* in, int n_in, uint8_t* out, int n_out
   return 0;
 }
 
+// GLV decomposition used by signing: k (32 bytes big-endian, any value; reduced mod r first like Fr::from_slice) ->
+// |k1|, |k2| as 4 little-endian u32 limbs each, signs in sg[0], sg[1]
+API void hs_glv_decompose(const uint8_t* k_be, uint32_t* k1, uint32_t* k2, uint8_t* sg) {
+  uint32_t k[8];
+  fr_reduce(k, k_be);
+  bool n1, n2;
+  glv_decompose(k1, &n1, k2, &n2, k);
+  sg[0] = n1; sg[1] = n2;
+}
+
 // randomised batch verification, one item's share: c * H(msg) (raw) and c * sig (raw) ; returns the ride / no-ride status
 API int hs_rlc_prepare(const uint8_t* msg, size_t len, const uint8_t* sig, const uint8_t* pk, const uint8_t* c16, int check_g2,
                        uint8_t* hs_out, uint8_t* sigc_out) {

@@ -353,3 +353,24 @@ def test_sign_glv_edge_scalars(hs):
         out = buf(64)
         assert hs.hs_sign(msg, len(msg), be(k), out) == 0
         assert out.raw == O.sign(msg, be(k))[1], hex(k)
+
+
+def test_glv_decomposition_identity_and_bounds(hs):
+    """k = k1 + k2 * lambda (mod r) with |k1|, |k2| < 2^128 (32 four-bit windows) for every scalar the signing path can see:
+    random 256-bit inputs (reduced mod r first) and the values around the lattice's corners."""
+    lam = 0xb3c4d79d41a917585bfc41088d8daaa78b17ea66b99c90dd
+    a1, b1n, a2, b2 = 0x89d3256894d213e3, 0x6f4d8248eeb859fc8211bbeb7d4f1128, 0x6f4d8248eeb859fd0be4e1541221250b, 0x89d3256894d213e3
+    assert (lam * lam + lam + 1) % R == 0 and (a1 - b1n * lam) % R == 0 and (a2 + b2 * lam) % R == 0
+    rng = random.Random(31)
+    ks = [0, 1, R - 1, R, R + 1, (1 << 256) - 1, lam, R - lam, a1, a2, b1n, a1 * a2 % R, R // 2, R // 2 + 1]
+    ks += [(i * a1 + j * a2) % R for i in range(-2, 3) for j in range(-2, 3)]
+    ks += [rng.randrange(1 << 256) for _ in range(20000)]
+    k1, k2, sg = (ctypes.c_uint32 * 4)(), (ctypes.c_uint32 * 4)(), (ctypes.c_uint8 * 2)()
+    worst = 0
+    for k in ks:
+        hs.hs_glv_decompose(be(k), k1, k2, sg)
+        v1 = sum(int(k1[i]) << (32 * i) for i in range(4)) * (-1 if sg[0] else 1)
+        v2 = sum(int(k2[i]) << (32 * i) for i in range(4)) * (-1 if sg[1] else 1)
+        assert (v1 + v2 * lam - k) % R == 0, hex(k)
+        worst = max(worst, abs(v1).bit_length(), abs(v2).bit_length())
+    assert worst <= 128   # the magnitudes are returned in four limbs, so anything larger would already have failed the identity
