@@ -280,7 +280,7 @@ def run_engine(args):
         "data": "synthetic",
         "config": {"workload": "batch verify 2^20 independent (32-byte msg, sig, pk) triples per GPU (BASELINE configs[1])",
                    "triples_per_gpu": n, "msg_len": 32, "l2": "inputs+workspace (%.0f MB) larger than L2" % ((224 + 448) * n / 1e6),
-                   "pairings_per_sec": value * 2, "pairing_kernels": "cooperative (six warps per 32 items), chunks of 2^17"},
+                   "pairings_per_sec": value * 2, "pairing_kernels": "cooperative machine: six warps per 32-item group, four groups per block (one per SM sub-partition), chunks of 2^17"},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 224 * n, "d2h_bytes_per_step": n, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches, "clocks": sampler.result(), "roofline": roof,
         "cpu_baseline": cpu_line,

@@ -321,6 +321,9 @@ __global__ void __launch_bounds__(BN_BLOCK, BN_LINES_MINB) k_verify_lines(const 
 #ifndef BN_COOP_STAGGER
 #define BN_COOP_STAGGER 0
 #endif
+#ifndef BN_COOP_DEFAULT_GROUPS4
+#define BN_COOP_DEFAULT_GROUPS4 1
+#endif
 #ifndef BN_COOP_DEFAULT_W
 #define BN_COOP_DEFAULT_W false
 #endif
@@ -363,6 +366,49 @@ __global__ void __launch_bounds__(COOP_THREADS, BN_COOP_MINB) k_coop_run(int whi
     COOP_BARRIER();
     coop_phase_b(c, ins, t, line_next);
     COOP_BARRIER();
+  }
+}
+
+// ---- the same block-layout machine with FOUR 32-item groups in one 24-warp block (one block per SM).  Warp w of a block
+// runs on sub-partition w % 4, so making group g = warps {g, g + 4, ..., g + 20} puts the six warps of a group on ONE
+// sub-partition: they share one multiplier pipe fairly, reach the group barrier together, and never wait for a sibling that
+// is queued behind other groups' warps on a busier sub-partition (in k_coop_run a block's warps are spread over all four
+// sub-partitions and 36 % of the warp-time is spent at the block barrier).  Barriers are per group (named barrier g + 1).
+#define COOP4_GROUPS 4
+#define COOP4_THREADS (COOP4_GROUPS * COOP_THREADS)
+#define COOP4_SMEM_BYTES (COOP4_GROUPS * COOP_SMEM_BYTES)
+__global__ void __launch_bounds__(COOP4_THREADS, 1) k_coop4_run(int which, size_t n, size_t n_pad, const u4* __restrict__ lines,
+                                                                u4* __restrict__ gslots, u4* __restrict__ fio,
+                                                                uint8_t* __restrict__ status) {
+  extern __shared__ u4 coop_sm[];
+  // (measured alternative: two groups sharing two sub-partitions, three warps of each on either, so that one group's commit
+  // phase is covered by the other's accumulation -- no faster than k_coop_run: the cross-sub-partition waiting is back)
+  const int warp = threadIdx.x >> 5, g = warp & (COOP4_GROUPS - 1);
+  coop_ctx c;
+  c.k = warp / COOP4_GROUPS;
+  c.lane = threadIdx.x & 31;
+  c.sm = coop_sm + g * (COOP_SLOTS * 2 * COOP_LANES) + c.lane;
+  c.row = COOP_LANES;
+  c.wmode = false;
+  c.plans = K_COOP_PLANS;
+  c.item = ((size_t)blockIdx.x * COOP4_GROUPS + g) * COOP_LANES + c.lane;
+  c.active = c.item < n;
+  c.n_pad = n_pad;
+  c.lines = lines;
+  c.gslots = gslots;
+  c.fio = fio;
+  c.status = status;
+  const uint32_t* prog = which == 0 ? K_COOP_PROG_VERIFY : which == 1 ? K_COOP_PROG_MILLER1 : which == 2 ? K_COOP_PROG_MILLER2 : which == 3 ? K_COOP_PROG_FINALEXP : K_COOP_PROG_MULTI;
+  int line_next = 0;
+  const int bar = g + 1;
+#pragma unroll 1
+  for (int pc = 0;; pc++) {
+    const uint32_t ins = prog[pc];
+    if ((ins & 0xff) == COP_END) break;
+    fq2 t = coop_phase_a(c, ins, line_next);
+    asm volatile("bar.sync %0, %1;" ::"r"(bar), "n"(COOP_THREADS) : "memory");
+    coop_phase_b(c, ins, t, line_next);
+    asm volatile("bar.sync %0, %1;" ::"r"(bar), "n"(COOP_THREADS) : "memory");
   }
 }
 
@@ -641,10 +687,12 @@ struct bn254_ctx {
   aff<fq>* d_comb_g1 = nullptr;   // (d + 1) * 16^w * G1 generator
   aff<fq2>* d_comb_g2 = nullptr;  // (d + 1) * 16^w * G2 generator
   uint64_t launches = 0;
-  // 0: cooperative machine (coop.cuh) in its default layout, 1: one thread per item (pairing.cuh),
-  // 2: cooperative, block layout (six warps per 32 items), 3: cooperative, warp-local layout (six lanes per item)
+  // 0: cooperative machine (coop.cuh) in its default form (block layout, four groups per block, one per sub-partition),
+  // 1: one thread per item (pairing.cuh), 2: cooperative, block layout with one 32-item group per six-warp block,
+  // 3: cooperative, warp-local layout (six lanes per item)
   int pairing_mode = 0;
   unsigned coop_stagger = BN_COOP_STAGGER;  // start offset between co-resident blocks of k_coop_run, SM cycles
+  int coop_groups4 = BN_COOP_DEFAULT_GROUPS4;  // block layout: four groups per 24-warp block, one group per sub-partition (k_coop4_run)
   bool coop_w = BN_COOP_DEFAULT_W;  // layout mode 0 uses for verify (BN254_COOP_W=0/1 in the environment overrides)
   std::string err;
   // optional per-phase timing of the verify pipeline (bn254_set_profiling): events recorded on `stream`
@@ -696,6 +744,7 @@ int bn254_ctx_create(int device, bn254_ctx** out) {
   bn254_ctx* ctx = new bn254_ctx();
   ctx->device = device;
   if (const char* w = getenv("BN254_COOP_W")) ctx->coop_w = w[0] == '1';
+  if (const char* w = getenv("BN254_COOP_GROUPS4")) ctx->coop_groups4 = atoi(w);
   if (const char* w = getenv("BN254_COOP_STAGGER")) ctx->coop_stagger = (unsigned)atoi(w);  // tuning knob (cycles)
   auto fail = [&](const char* what, cudaError_t ee) {
     g_create_err = std::string(what) + ": " + cudaGetErrorString(ee);
@@ -727,6 +776,8 @@ int bn254_ctx_create(int device, bn254_ctx** out) {
     return fail("cudaFuncSetAttribute(k_coop_run)", e);
   if ((e = cudaFuncSetAttribute(k_coopw_run, cudaFuncAttributeMaxDynamicSharedMemorySize, COOPW_SMEM_BYTES)) != cudaSuccess)
     return fail("cudaFuncSetAttribute(k_coopw_run)", e);
+  if ((e = cudaFuncSetAttribute(k_coop4_run, cudaFuncAttributeMaxDynamicSharedMemorySize, COOP4_SMEM_BYTES)) != cudaSuccess)
+    return fail("cudaFuncSetAttribute(k_coop4_run)", e);
   *out = ctx;
   return 0;
 }
@@ -885,6 +936,21 @@ int bn254_sign_batch(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, const 
   return 0;
 }
 
+// one launch of the block-layout cooperative machine over `groups` 32-item groups: four groups per 24-warp block (one per
+// sub-partition, k_coop4_run) unless the context asks for the one-group-per-block kernel (pairing mode 2)
+static int launch_coop_groups(bn254_ctx* ctx, int which, size_t n, size_t n_pad, const u4* lines, u4* gslots, u4* fio, uint8_t* status,
+                              size_t groups) {
+  if (ctx->pairing_mode == 2 || !ctx->coop_groups4)
+    k_coop_run<<<(unsigned)groups, COOP_THREADS, COOP_SMEM_BYTES, ctx->stream>>>(which, n, n_pad, lines, gslots, fio, status, ctx->coop_stagger,
+                                                                                (unsigned)ctx->sm_count);
+  else
+    k_coop4_run<<<(unsigned)((groups + COOP4_GROUPS - 1) / COOP4_GROUPS), COOP4_THREADS, COOP4_SMEM_BYTES, ctx->stream>>>(which, n, n_pad, lines,
+                                                                                                                        gslots, fio, status);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
 // msgs == NULL: check_public_keys form (first G1 argument = generator, no hashing)
 static int verify_dev_impl(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, const uint8_t* sigs, const uint8_t* pks, size_t n,
                            uint8_t* status) {
@@ -928,11 +994,14 @@ static int verify_dev_impl(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, 
       if (wl)
         k_coopw_run<<<(unsigned)((m + COOPW_ITEMS - 1) / COOPW_ITEMS), COOPW_WARPS * 32, COOPW_SMEM_BYTES, ctx->stream>>>(
             0, m, m_pad, LN.as<u4>(), GS.as<u4>(), (u4*)nullptr, status + off);
-      else
-        k_coop_run<<<(unsigned)(m_pad / COOP_LANES), COOP_THREADS, COOP_SMEM_BYTES, ctx->stream>>>(0, m, m_pad, LN.as<u4>(), GS.as<u4>(),
-                                                                                                    (u4*)nullptr, status + off, ctx->coop_stagger, (unsigned)ctx->sm_count);
-      ctx->launches++;
-      CK(cudaGetLastError());
+      else {
+        int rc = launch_coop_groups(ctx, 0, m, m_pad, LN.as<u4>(), GS.as<u4>(), (u4*)nullptr, status + off, m_pad / COOP_LANES);
+        if (rc) return rc;
+      }
+      if (wl) {
+        ctx->launches++;
+        CK(cudaGetLastError());
+      }
       CK(mark());
     } else {
       LAUNCH(k_verify_miller, grid_for(m), BN_BLOCK, h, sigs + 64 * off, pks + 128 * off, m, F.as<fq12>(), status + off, ctx->d_lines);
@@ -1197,9 +1266,10 @@ static int distinct_partial_points_dev(bn254_ctx* ctx, g1aff* H_p, uint8_t* hst_
       size_t blocks = (m + per_block - 1) / per_block, L = blocks * COOP_LANES;
       LAUNCH(k_pair_lines, grid_for(L * COOP_MULTI_K), BN_BLOCK, H.as<g1aff>() + off, hst.as<uint8_t>() + off, pks + 128 * off, m, L, LN.as<u4>(),
              err.as<unsigned long long>(), off);
-      k_coop_run<<<(unsigned)blocks, COOP_THREADS, COOP_SMEM_BYTES, ctx->stream>>>(4, L, L, LN.as<u4>(), (u4*)nullptr, FIO.as<u4>(), (uint8_t*)nullptr, ctx->coop_stagger, (unsigned)ctx->sm_count);
-      ctx->launches++;
-      CK(cudaGetLastError());
+      {
+        int rc2 = launch_coop_groups(ctx, 4, L, L, LN.as<u4>(), (u4*)nullptr, FIO.as<u4>(), (uint8_t*)nullptr, blocks);
+        if (rc2) return rc2;
+      }
       LAUNCH(k_coop_gather, grid_for(blocks), BN_BLOCK, FIO.as<u4>(), L, blocks, partial.as<fq12>() + done_blocks);
       done_blocks += blocks;
     }

@@ -67,10 +67,10 @@ uint64_t bn254_launch_count(bn254_ctx* ctx);   /* kernels launched by this conte
  * Miller + final exponentiation with mode 0 */
 int bn254_set_profiling(bn254_ctx* ctx, int on);
 int bn254_phase_ms(bn254_ctx* ctx, float* out3);
-/* pairing kernels used by verify / check_public_keys: 0 (default) = cooperative machine (csrc/coop.cuh) in its default
- * layout; 1 = one thread per item (csrc/pairing.cuh); 2 = cooperative, block layout (six warps share the Fq12 values of 32
- * items); 3 = cooperative, warp-local layout (six lanes share the Fq12 value of one item, five items per warp).  All give
- * identical verdicts (tests compare them). */
+/* pairing kernels used by verify / check_public_keys: 0 (default) = cooperative machine (csrc/coop.cuh), six warps share the
+ * Fq12 values of a 32-item group, four groups per 24-warp block so that each group owns one SM sub-partition; 1 = one thread
+ * per item (csrc/pairing.cuh); 2 = cooperative, one group per six-warp block; 3 = cooperative, warp-local layout (six lanes
+ * share the Fq12 value of one item, five items per warp).  All give identical verdicts (tests compare them). */
 int bn254_set_pairing_mode(bn254_ctx* ctx, int mode);
 
 /* hash_to_try_and_increment (/root/reference/src/hash.rs:29-63): n messages of msg_len bytes each -> G1 */
