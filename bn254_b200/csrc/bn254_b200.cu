@@ -324,6 +324,9 @@ __global__ void __launch_bounds__(BN_BLOCK, BN_LINES_MINB) k_verify_lines(const 
 #ifndef BN_COOP_DEFAULT_GROUPS4
 #define BN_COOP_DEFAULT_GROUPS4 1
 #endif
+#ifndef BN_COOP_DEFAULT_H
+#define BN_COOP_DEFAULT_H false
+#endif
 #ifndef BN_COOP_DEFAULT_W
 #define BN_COOP_DEFAULT_W false
 #endif
@@ -379,7 +382,7 @@ __global__ void __launch_bounds__(COOP_THREADS, BN_COOP_MINB) k_coop_run(int whi
 #define COOP4_SMEM_BYTES (COOP4_GROUPS * COOP_SMEM_BYTES)
 __global__ void __launch_bounds__(COOP4_THREADS, 1) k_coop4_run(int which, size_t n, size_t n_pad, const u4* __restrict__ lines,
                                                                 u4* __restrict__ gslots, u4* __restrict__ fio,
-                                                                uint8_t* __restrict__ status) {
+                                                                uint8_t* __restrict__ status, unsigned stagger_ns) {
   extern __shared__ u4 coop_sm[];
   // (measured alternative: two groups sharing two sub-partitions, three warps of each on either, so that one group's commit
   // phase is covered by the other's accumulation -- no faster than k_coop_run: the cross-sub-partition waiting is back)
@@ -405,10 +408,66 @@ __global__ void __launch_bounds__(COOP4_THREADS, 1) k_coop4_run(int which, size_
   for (int pc = 0;; pc++) {
     const uint32_t ins = prog[pc];
     if ((ins & 0xff) == COP_END) break;
+    // The six warps of a group leave the barrier together and the scheduler keeps them in step, so their multiply-free
+    // stretches (operand loads, reduction fix-ups, recombination) would coincide and leave the multiplier pipe idle while
+    // the ALU pipe is busy, and vice versa.  One warp in its accumulation phase saturates the pipe on its own, so warp k
+    // starts k * stagger_ns late: the warps stay offset through the phase and each one's ALU work hides under another's
+    // multiply-adds; the early finishers simply wait at the barrier.
+    if (stagger_ns && (ins & 0xff) == COP_DOT && c.k) __nanosleep(c.k * stagger_ns);
     fq2 t = coop_phase_a(c, ins, line_next);
     asm volatile("bar.sync %0, %1;" ::"r"(bar), "n"(COOP_THREADS) : "memory");
     coop_phase_b(c, ins, t, line_next);
     asm volatile("bar.sync %0, %1;" ::"r"(bar), "n"(COOP_THREADS) : "memory");
+  }
+}
+
+// ---- half-warp layout: a group is 16 items and THREE warps, each warp carrying two coefficients (lanes 0-15 one, lanes
+// 16-31 the other), so the 24 warps of a block form EIGHT groups, two per sub-partition.  Same shared memory per item and
+// the same warp count as k_coop4_run, but while one group of a sub-partition is in its multiply-free stretch (recombination,
+// commit of the records, barriers) the other one can be accumulating: in k_coop4_run the six warps of a sub-partition move in
+// step, so that stretch -- a quarter of the kernel's time -- leaves the multiplier pipe idle.  Coefficient pairs (0,2), (1,3),
+// (4,5): squares and cyclotomic squares need one product more for even coefficients, so only the third warp pays for a mixed pair.
+#define COOPH_GROUPS 8
+#define COOPH_GROUP_THREADS 96
+#define COOPH_GROUP_U4 (COOP_SLOTS * 2 * COOPH_ROW)
+#define COOPH_SMEM_BYTES (COOPH_GROUPS * COOPH_GROUP_U4 * 16)
+__global__ void __launch_bounds__(COOP4_THREADS, 1) k_cooph_run(int which, size_t n, size_t n_pad, const u4* __restrict__ lines,
+                                                                u4* __restrict__ gslots, u4* __restrict__ fio,
+                                                                uint8_t* __restrict__ status, unsigned offset_cycles) {
+  extern __shared__ u4 coop_sm[];
+  const int warp = threadIdx.x >> 5, sp = warp & 3, j = warp >> 2;  // sub-partition of this warp and its slot there
+  const int g = sp + 4 * (j / 3), p = j % 3, L = threadIdx.x & 31;
+  coop_ctx c;
+  c.k = p == 0 ? (L < 16 ? 0 : 2) : p == 1 ? (L < 16 ? 1 : 3) : (L < 16 ? 4 : 5);
+  c.lane = L & 15;
+  c.sm = coop_sm + g * COOPH_GROUP_U4 + c.lane;
+  c.row = COOPH_ROW;
+  c.wmode = false;
+  c.plans = K_COOP_PLANS_H;
+  c.item = ((size_t)blockIdx.x * COOPH_GROUPS + g) * COOPH_ROW + c.lane;
+  c.active = c.item < n;
+  c.n_pad = n_pad;
+  c.lines = lines;
+  c.gslots = gslots;
+  c.fio = fio;
+  c.status = status;
+  const uint32_t* prog = which == 0 ? K_COOP_PROG_VERIFY : which == 1 ? K_COOP_PROG_MILLER1 : which == 2 ? K_COOP_PROG_MILLER2 : K_COOP_PROG_FINALEXP;
+  // the second group of every sub-partition starts late, so that the two do not run their phases in step
+  if (offset_cycles && g >= 4) {
+    const long long t0 = clock64();
+    while (clock64() - t0 < (long long)offset_cycles) {
+    }
+  }
+  int line_next = 0;
+  const int bar = g + 1;
+#pragma unroll 1
+  for (int pc = 0;; pc++) {
+    const uint32_t ins = prog[pc];
+    if ((ins & 0xff) == COP_END) break;
+    fq2 t = coop_phase_a(c, ins, line_next);
+    asm volatile("bar.sync %0, %1;" ::"r"(bar), "n"(COOPH_GROUP_THREADS) : "memory");
+    coop_phase_b(c, ins, t, line_next);
+    asm volatile("bar.sync %0, %1;" ::"r"(bar), "n"(COOPH_GROUP_THREADS) : "memory");
   }
 }
 
@@ -693,6 +752,7 @@ struct bn254_ctx {
   int pairing_mode = 0;
   unsigned coop_stagger = BN_COOP_STAGGER;  // start offset between co-resident blocks of k_coop_run, SM cycles
   int coop_groups4 = BN_COOP_DEFAULT_GROUPS4;  // block layout: four groups per 24-warp block, one group per sub-partition (k_coop4_run)
+  bool coop_h = BN_COOP_DEFAULT_H;  // verify uses the half-warp layout (k_cooph_run, pairing mode 4)
   bool coop_w = BN_COOP_DEFAULT_W;  // layout mode 0 uses for verify (BN254_COOP_W=0/1 in the environment overrides)
   std::string err;
   // optional per-phase timing of the verify pipeline (bn254_set_profiling): events recorded on `stream`
@@ -744,6 +804,7 @@ int bn254_ctx_create(int device, bn254_ctx** out) {
   bn254_ctx* ctx = new bn254_ctx();
   ctx->device = device;
   if (const char* w = getenv("BN254_COOP_W")) ctx->coop_w = w[0] == '1';
+  if (const char* w = getenv("BN254_COOP_H")) ctx->coop_h = w[0] == '1';
   if (const char* w = getenv("BN254_COOP_GROUPS4")) ctx->coop_groups4 = atoi(w);
   if (const char* w = getenv("BN254_COOP_STAGGER")) ctx->coop_stagger = (unsigned)atoi(w);  // tuning knob (cycles)
   auto fail = [&](const char* what, cudaError_t ee) {
@@ -778,6 +839,8 @@ int bn254_ctx_create(int device, bn254_ctx** out) {
     return fail("cudaFuncSetAttribute(k_coopw_run)", e);
   if ((e = cudaFuncSetAttribute(k_coop4_run, cudaFuncAttributeMaxDynamicSharedMemorySize, COOP4_SMEM_BYTES)) != cudaSuccess)
     return fail("cudaFuncSetAttribute(k_coop4_run)", e);
+  if ((e = cudaFuncSetAttribute(k_cooph_run, cudaFuncAttributeMaxDynamicSharedMemorySize, COOPH_SMEM_BYTES)) != cudaSuccess)
+    return fail("cudaFuncSetAttribute(k_cooph_run)", e);
   *out = ctx;
   return 0;
 }
@@ -945,7 +1008,8 @@ static int launch_coop_groups(bn254_ctx* ctx, int which, size_t n, size_t n_pad,
                                                                                 (unsigned)ctx->sm_count);
   else
     k_coop4_run<<<(unsigned)((groups + COOP4_GROUPS - 1) / COOP4_GROUPS), COOP4_THREADS, COOP4_SMEM_BYTES, ctx->stream>>>(which, n, n_pad, lines,
-                                                                                                                        gslots, fio, status);
+                                                                                                                        gslots, fio, status,
+                                                                                                                        ctx->coop_stagger);
   ctx->launches++;
   CK(cudaGetLastError());
   return 0;
@@ -956,6 +1020,7 @@ static int verify_dev_impl(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, 
                            uint8_t* status) {
   const bool coop = ctx->pairing_mode != 1;
   const bool wl = ctx->pairing_mode == 3 || (ctx->pairing_mode == 0 && ctx->coop_w);
+  const bool hl = !wl && (ctx->pairing_mode == 4 || (ctx->pairing_mode == 0 && ctx->coop_h));
   // chunking bounds the workspace: the cooperative path stores 174 line sets (50 KB) per item
   // (warp-local layout: a whole number of waves of 30-item blocks, so that the last wave of a chunk is not mostly empty)
   const size_t CHUNK = !coop ? ((size_t)1 << 20) : wl ? (size_t)ctx->sm_count * BN_COOP_MINB * COOPW_ITEMS * 7 : ((size_t)1 << 17);
@@ -994,11 +1059,14 @@ static int verify_dev_impl(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, 
       if (wl)
         k_coopw_run<<<(unsigned)((m + COOPW_ITEMS - 1) / COOPW_ITEMS), COOPW_WARPS * 32, COOPW_SMEM_BYTES, ctx->stream>>>(
             0, m, m_pad, LN.as<u4>(), GS.as<u4>(), (u4*)nullptr, status + off);
+      else if (hl)
+        k_cooph_run<<<(unsigned)((m_pad / COOPH_ROW + COOPH_GROUPS - 1) / COOPH_GROUPS), COOP4_THREADS, COOPH_SMEM_BYTES, ctx->stream>>>(
+            0, m, m_pad, LN.as<u4>(), GS.as<u4>(), (u4*)nullptr, status + off, ctx->coop_stagger);
       else {
         int rc = launch_coop_groups(ctx, 0, m, m_pad, LN.as<u4>(), GS.as<u4>(), (u4*)nullptr, status + off, m_pad / COOP_LANES);
         if (rc) return rc;
       }
-      if (wl) {
+      if (wl || hl) {
         ctx->launches++;
         CK(cudaGetLastError());
       }
@@ -1014,7 +1082,7 @@ static int verify_dev_impl(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, 
 }
 int bn254_set_pairing_mode(bn254_ctx* ctx, int mode) {
   ENTER();
-  ARGCHECK(mode >= 0 && mode <= 3);
+  ARGCHECK(mode >= 0 && mode <= 4);
   ctx->pairing_mode = mode;
   return 0;
 }

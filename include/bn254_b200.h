@@ -70,7 +70,9 @@ int bn254_phase_ms(bn254_ctx* ctx, float* out3);
 /* pairing kernels used by verify / check_public_keys: 0 (default) = cooperative machine (csrc/coop.cuh), six warps share the
  * Fq12 values of a 32-item group, four groups per 24-warp block so that each group owns one SM sub-partition; 1 = one thread
  * per item (csrc/pairing.cuh); 2 = cooperative, one group per six-warp block; 3 = cooperative, warp-local layout (six lanes
- * share the Fq12 value of one item, five items per warp).  All give identical verdicts (tests compare them). */
+ * share the Fq12 value of one item, five items per warp); 4 = cooperative, half-warp layout (three warps per 16-item group,
+ * two coefficients per warp, two groups per sub-partition).  All give identical verdicts (tests compare them); 2 - 4 are
+ * the measured design alternatives of DESIGN.md 4.3, slower than the default. */
 int bn254_set_pairing_mode(bn254_ctx* ctx, int mode);
 
 /* hash_to_try_and_increment (/root/reference/src/hash.rs:29-63): n messages of msg_len bytes each -> G1 */

@@ -382,6 +382,7 @@ def wnaf(n, w):
 
 
 WROW = 5  # items per warp in the warp-local layout (6 coefficients x 5 items = 30 lanes)
+HROW = 16  # items per group in the half-warp layout (a warp = two coefficients x 16 items)
 EXP_TMP_SLOT = 6  # global slot that holds base^3 during an exponentiation
 
 
@@ -559,9 +560,10 @@ def gen_tables():
     o.append("#define COOP_DEST_NONE %d" % DEST_NONE)
     o.append("// plan row: word 0 = n | double-X mask << 4 | negate-X mask << 10 | dest << 16 | post << 20 | (weight <= 3) << 24 ;")
     o.append("// words 1..6 = byte offset of the X triple | byte offset of the Y triple << 16 (slot * slot bytes: 1024 in the")
-    o.append("// block layout = 32 items per row, %d in the warp-local layout = %d items per row)" % (32 * WROW, WROW))
+    o.append("// block layout = 32 items per row, %d in the warp-local layout = %d items per row, %d in the half-warp layout)" % (32 * WROW, WROW, 32 * HROW))
     o.append("#define COOPW_ROW %d" % WROW)
-    for tname, slot_bytes in (("K_COOP_PLANS", 1024), ("K_COOP_PLANS_W", 32 * WROW)):
+    o.append("#define COOPH_ROW %d" % HROW)
+    for tname, slot_bytes in (("K_COOP_PLANS", 1024), ("K_COOP_PLANS_W", 32 * WROW), ("K_COOP_PLANS_H", 32 * HROW)):
         o.append("BN_CONST uint32_t %s[CPLAN_COUNT][6][7] = {" % tname)
         for name, fn in PLANS:
             rows = fn()

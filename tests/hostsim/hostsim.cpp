@@ -194,22 +194,23 @@ API int hs_rlc_prepare(const uint8_t* msg, size_t len, const uint8_t* sig, const
 #include "../../bn254_b200/csrc/coop_lines.cuh"
 #include <vector>
 
-static int g_coop_wmode = 0;  // 0: block layout (32 items per row, warp k = coefficient k), 1: warp-local layout (5 items per row)
+static int g_coop_wmode = 0;  // 0: block layout (32 items per row, warp k = coefficient k), 1: warp-local layout (5 items per row),
+                              // 2: half-warp layout (16 items per row, two coefficients per warp)
 API void hs_coop_set_layout(int wmode) { g_coop_wmode = wmode; }
 
 struct coop_sim {
   std::vector<u4> sm, lines, gslots, fio;
   uint8_t status = 0;
   size_t n_pad = COOP_LANES;
-  bool wmode = g_coop_wmode != 0;
-  int row = wmode ? COOPW_ROW : COOP_LANES;
+  bool wmode = g_coop_wmode == 1;
+  int row = g_coop_wmode == 1 ? COOPW_ROW : g_coop_wmode == 2 ? COOPH_ROW : COOP_LANES;
   coop_sim() : sm(COOP_SLOTS * 2 * COOP_LANES), lines((size_t)COOP_MULTI_K * K_N_LINES * COOP_LINE_FQ * 2 * COOP_LANES),
                gslots((size_t)COOP_GSLOTS * 6 * 2 * 2 * COOP_LANES), fio((size_t)6 * 2 * 2 * COOP_LANES) {}
   int lanes = 1;  // simulated items of the group (32 for the multi-pairing butterfly, block layout only)
   int line_next[COOP_WARPS][COOP_LANES] = {};
   coop_ctx ctx(int k, int lane) {
     coop_ctx c;
-    c.sm = sm.data() + lane; c.row = row; c.wmode = wmode; c.plans = wmode ? K_COOP_PLANS_W : K_COOP_PLANS;
+    c.sm = sm.data() + lane; c.row = row; c.wmode = wmode; c.plans = g_coop_wmode == 1 ? K_COOP_PLANS_W : g_coop_wmode == 2 ? K_COOP_PLANS_H : K_COOP_PLANS;
     c.k = k; c.lane = lane; c.active = true; c.item = lane; c.n_pad = n_pad;
     c.lines = lines.data(); c.gslots = gslots.data(); c.fio = fio.data(); c.status = &status;
     return c;

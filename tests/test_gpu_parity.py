@@ -465,18 +465,18 @@ def test_pairing_modes_agree_on_ragged_batches(E):
     want = O.verify_batch(msgs, 32, sigs, pks, n, NTHREADS)
     # modes 2 / 3: the cooperative machine in its block layout (32-item groups) and its warp-local layout (5 items per
     # warp, 30 per block): sizes around both group sizes
-    for size in (1000, 1, 4, 5, 6, 29, 30, 31, 33, 95):
+    for size in (1000, 1, 4, 5, 6, 15, 16, 17, 29, 30, 31, 33, 95, 127, 129):
         got = {}
-        for mode in (0, 1, 2, 3):
+        for mode in (0, 1, 2, 3, 4):
             ctx.call("bn254_set_pairing_mode", I(mode))
             got[mode] = E.verify_batch(msgs[:32 * size], 32, sigs[:64 * size], pks[:128 * size], ctx=ctx)
         ctx.call("bn254_set_pairing_mode", I(0))
-        assert got[0] == got[1] == got[2] == got[3] == want[:size], size
+        assert got[0] == got[1] == got[2] == got[3] == got[4] == want[:size], size
     # check_public_keys goes through the same two paths (generator instead of H(m))
     pk1 = E.derive_pk_g1_batch(sks[:32 * 40], ctx=ctx)
     pk2 = bytearray(pks[:128 * 40])
     pk2[128 * 3:128 * 4] = pks[128 * 4:128 * 5]
-    for mode in (0, 1, 2, 3):
+    for mode in (0, 1, 2, 3, 4):
         ctx.call("bn254_set_pairing_mode", I(mode))
         st = E.check_public_keys_batch(bytes(pk2), pk1, ctx=ctx)
         assert st[3] == O.VERIFICATION_FAILED and st[7] != 0 and sum(1 for s in st if s == 0) == 38, (mode, st)

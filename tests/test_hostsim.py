@@ -221,10 +221,10 @@ def test_codecs(hs):
 
 
 # ---------------------------------------------------------------------------------------------- cooperative machine
-@pytest.fixture(params=[0, 1], ids=["block-layout", "warp-local-layout"])
+@pytest.fixture(params=[0, 1, 2], ids=["block-layout", "warp-local-layout", "half-warp-layout"])
 def layout(hs, request):
-    """Both shared-memory layouts of the machine run the same programs: six warps per 32 items (k_coop_run) and six lanes
-    per item, five items per warp (k_coopw_run)."""
+    """All shared-memory layouts of the machine run the same programs: six warps per 32 items (k_coop_run / k_coop4_run), six
+    lanes per item with five items per warp (k_coopw_run), three warps per 16 items (k_cooph_run)."""
     hs.hs_coop_set_layout(request.param)
     yield request.param
     hs.hs_coop_set_layout(0)
