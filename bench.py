@@ -9,7 +9,7 @@ A step = one pass of ECDSA::verify over a batch of 2^20 independent (32-byte msg
               engine's stream, max over ranks)
   e2e         the same metric through the public host-buffer entry point (bn254_verify_batch via
               bn254_b200.engine.verify_batch): pinned host inputs, H2D + kernels + D2H of the verdicts timed
-  roofline    INT32 multiply-pipe roofline of the dominant kernel (k_coop_run: Miller accumulation + final
+  roofline    INT32 multiply-pipe roofline of the dominant kernel (k_coop4_run: Miller accumulation + final
               exponentiation): achieved = algorithmic IMAD32 (264 per Fq product) per second over the
               kernel's CUDA-event time, peak = the IMAD issue rate measured live by tools/microbench.bin on this GPU
               (the path is integer-issue bound: a verify reads 224 B and does ~5.8 M IMAD32-equivalents, so neither
@@ -34,7 +34,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 # does the work in the cooperative pipeline:
 M_HASH = 774            # k_hash_to_g1: try-and-increment, 2.116 expected tries
 M_LINES = 3083          # k_verify_lines: G2 doubling / addition steps (64 x 28 + 23 x 41) + scaling of the -G2 lines (87 x 4)
-M_COOP = 18028          # k_coop_run: f^2 chain 2 304 + 2 x 87 sparse products x 39 + final exponentiation 8 938
+M_COOP = 18028          # k_coop4_run: f^2 chain 2 304 + 2 x 87 sparse products x 39 + final exponentiation 8 938
 M_VERIFY = M_HASH + M_LINES + M_COOP
 IMAD_PER_M = 264        # IMAD32 issue slots per Fq product (an IMAD.WIDE.U32.X costs two: profiles/r01_tuning_log.md)
 METRIC = "bn254_verifies_per_sec"
@@ -245,22 +245,22 @@ def run_engine(args):
     achieved = (n * M_COOP * IMAD_PER_M / (coop_ms * 1e-3) / 1e9) if coop_ms > 0 else None
     step_ms = ms_total / args.steps
     traffic, hbm = None, None
-    try:  # DRAM bytes of one k_coop_run launch from the committed ncu capture (not measured live)
+    try:  # DRAM bytes of one k_coop4_run launch from the committed ncu capture (not measured live)
         tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-        traffic = tj["k_coop_run"]["dram_bytes_per_launch"]
+        traffic = tj["k_coop4_run"]["dram_bytes_per_launch"]
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
         launch_ms = coop_ms / max(1, (n + (1 << 17) - 1) >> 17)
         items = min(n, 1 << 17)
-        hbm = {"achieved_gbs": traffic * items / tj["k_coop_run"]["items_per_launch"] / (launch_ms * 1e-3) / 1e9,
+        hbm = {"achieved_gbs": traffic * items / tj["k_coop4_run"]["items_per_launch"] / (launch_ms * 1e-3) / 1e9,
                "peak_gbs": peaks.get("hbm_gbs", 6650.0), "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"}
         hbm["frac"] = hbm["achieved_gbs"] / hbm["peak_gbs"]
     except Exception:
         pass
     roof = {
-        "bound": "int32_imad", "kernel": "k_coop_run", "achieved": achieved, "peak": peak, "unit": "GIMAD32/s",
+        "bound": "int32_imad", "kernel": "k_coop4_run", "achieved": achieved, "peak": peak, "unit": "GIMAD32/s",
         "frac": (achieved / peak if achieved and peak else None), "traffic": traffic,
         "peak_source": "tools/microbench.bin mad.lo.u32 chain measured in this run (MEASURED_PEAKS.json has no int32 figure)",
-        "algorithmic_per_unit": {"k_hash_to_g1": M_HASH * IMAD_PER_M, "k_verify_lines": M_LINES * IMAD_PER_M, "k_coop_run": M_COOP * IMAD_PER_M,
+        "algorithmic_per_unit": {"k_hash_to_g1": M_HASH * IMAD_PER_M, "k_verify_lines": M_LINES * IMAD_PER_M, "k_coop4_run": M_COOP * IMAD_PER_M,
                                  "unit": "IMAD32 per verify"},
         "whole_step_frac": (n * M_VERIFY * IMAD_PER_M / (step_ms * 1e-3) / 1e9 / peak) if peak else None,
         "phase_ms": {"hash_to_g1": phase[0], "line_sets": phase[1], "miller_and_final_exp": phase[2]},
