@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(BN_BLOCK) k_fq_op(int op, const uint8_t* __res
   fq x, y, r = fq_zero();
   int st = ST_OK;
   if (!fq_from_be(&x, a + 32 * i)) st = ST_NOT_MEMBER;
-  if (!st && (op <= 2 || op == 5) && !fq_from_be(&y, b + 32 * i)) st = ST_NOT_MEMBER;
+  if (!st && (op <= 2 || op >= 5) && !fq_from_be(&y, b + 32 * i)) st = ST_NOT_MEMBER;
   if (!st) {
     if (op == 0) r = fq_mul(x, y);
     else if (op == 1) r = fq_add(x, y);
@@ -218,6 +218,8 @@ __global__ void __launch_bounds__(BN_BLOCK) k_fq_op(int op, const uint8_t* __res
     else if (op == 3) r = fq_inv(x);
     else if (op == 4) { if (!fq_sqrt(&r, x)) st = ST_NOT_MEMBER; }
     else if (op == 5) r = fq_mul_portable(x, y);
+    else if (op == 6) r = fq_mul9_add(x, y, &K_KQ_TABLE[0][0]);              // 9 x + y
+    else if (op == 7) r = fq_mul9_add(x, fq_q_minus(y), &K_KQ_TABLE[0][0]);  // 9 x - y
     else st = ST_INVALID_ENCODING;
   }
   status[i] = (uint8_t)st;
@@ -352,6 +354,7 @@ __global__ void __launch_bounds__(COOP_THREADS, BN_COOP_MINB) k_coop_run(int whi
   c.row = COOP_LANES;
   c.wmode = false;
   c.plans = K_COOP_PLANS;
+  c.kq = nullptr;
   c.item = (size_t)blockIdx.x * COOP_LANES + c.lane;
   c.active = c.item < n;
   c.n_pad = n_pad;
@@ -379,7 +382,7 @@ __global__ void __launch_bounds__(COOP_THREADS, BN_COOP_MINB) k_coop_run(int whi
 // sub-partitions and 36 % of the warp-time is spent at the block barrier).  Barriers are per group (named barrier g + 1).
 #define COOP4_GROUPS 4
 #define COOP4_THREADS (COOP4_GROUPS * COOP_THREADS)
-#define COOP4_SMEM_BYTES (COOP4_GROUPS * COOP_SMEM_BYTES)
+#define COOP4_SMEM_BYTES (COOP4_GROUPS * COOP_SMEM_BYTES + 11 * 32) /* + the k q table of fq_mul9_add */
 __global__ void __launch_bounds__(COOP4_THREADS, 1) k_coop4_run(int which, size_t n, size_t n_pad, const u4* __restrict__ lines,
                                                                 u4* __restrict__ gslots, u4* __restrict__ fio,
                                                                 uint8_t* __restrict__ status, unsigned stagger_ns) {
@@ -387,6 +390,9 @@ __global__ void __launch_bounds__(COOP4_THREADS, 1) k_coop4_run(int which, size_
   // (measured alternative: two groups sharing two sub-partitions, three warps of each on either, so that one group's commit
   // phase is covered by the other's accumulation -- no faster than k_coop_run: the cross-sub-partition waiting is back)
   const int warp = threadIdx.x >> 5, g = warp & (COOP4_GROUPS - 1);
+  uint32_t* kq = (uint32_t*)(coop_sm + COOP4_GROUPS * (COOP_SLOTS * 2 * COOP_LANES));
+  if (threadIdx.x < 88) kq[threadIdx.x] = (&K_KQ_TABLE[0][0])[threadIdx.x];
+  __syncthreads();
   coop_ctx c;
   c.k = warp / COOP4_GROUPS;
   c.lane = threadIdx.x & 31;
@@ -394,6 +400,7 @@ __global__ void __launch_bounds__(COOP4_THREADS, 1) k_coop4_run(int which, size_
   c.row = COOP_LANES;
   c.wmode = false;
   c.plans = K_COOP_PLANS;
+  c.kq = (stagger_ns & 0x80000000u) ? nullptr : kq;  // tuning switch: top bit of the knob selects the additions-only xi variants
   c.item = ((size_t)blockIdx.x * COOP4_GROUPS + g) * COOP_LANES + c.lane;
   c.active = c.item < n;
   c.n_pad = n_pad;
@@ -413,7 +420,7 @@ __global__ void __launch_bounds__(COOP4_THREADS, 1) k_coop4_run(int which, size_
     // the ALU pipe is busy, and vice versa.  One warp in its accumulation phase saturates the pipe on its own, so warp k
     // starts k * stagger_ns late: the warps stay offset through the phase and each one's ALU work hides under another's
     // multiply-adds; the early finishers simply wait at the barrier.
-    if (stagger_ns && (ins & 0xff) == COP_DOT && c.k) __nanosleep(c.k * stagger_ns);
+    if ((stagger_ns & 0x7fffffffu) && (ins & 0xff) == COP_DOT && c.k) __nanosleep(c.k * (stagger_ns & 0x7fffffffu));
     fq2 t = coop_phase_a(c, ins, line_next);
     asm volatile("bar.sync %0, %1;" ::"r"(bar), "n"(COOP_THREADS) : "memory");
     coop_phase_b(c, ins, t, line_next);
@@ -444,6 +451,7 @@ __global__ void __launch_bounds__(COOP4_THREADS, 1) k_cooph_run(int which, size_
   c.row = COOPH_ROW;
   c.wmode = false;
   c.plans = K_COOP_PLANS_H;
+  c.kq = nullptr;
   c.item = ((size_t)blockIdx.x * COOPH_GROUPS + g) * COOPH_ROW + c.lane;
   c.active = c.item < n;
   c.n_pad = n_pad;
@@ -497,6 +505,7 @@ __global__ void __launch_bounds__(COOPW_WARPS * 32, BN_COOP_MINB) k_coopw_run(in
   c.row = COOPW_ROW;
   c.wmode = true;
   c.plans = (const uint32_t (*)[6][7])plans;
+  c.kq = nullptr;
   c.item = ((size_t)blockIdx.x * COOPW_WARPS + warp) * COOPW_ROW + c.lane;
   c.active = live && c.item < n;
   c.n_pad = n_pad;

@@ -167,6 +167,18 @@ API int hs_layer_op(int op, const uint8_t* in, int n_in, uint8_t* out, int n_out
   return 0;
 }
 
+// (9 x + z) mod q with one reduction (fq.cuh fq_mul9_add); x, z big-endian integers, z may equal q; plain (non-Montgomery) values
+API void hs_mul9_add(const uint8_t* x_be, const uint8_t* z_be, uint8_t* out_be) {
+  fq x, z;
+  u256_from_be(x.l, x_be);
+  u256_from_be(z.l, z_be);
+  fq r = fq_mul9_add(x, z, &K_KQ_TABLE[0][0]);
+  for (int i = 0; i < 8; i++) {
+    uint32_t w = r.l[7 - i];
+    out_be[4 * i] = (uint8_t)(w >> 24); out_be[4 * i + 1] = (uint8_t)(w >> 16); out_be[4 * i + 2] = (uint8_t)(w >> 8); out_be[4 * i + 3] = (uint8_t)w;
+  }
+}
+
 // GLV decomposition used by signing: k (32 bytes big-endian, any value; reduced mod r first like Fr::from_slice) ->
 // |k1|, |k2| as 4 little-endian u32 limbs each, signs in sg[0], sg[1]
 API void hs_glv_decompose(const uint8_t* k_be, uint32_t* k1, uint32_t* k2, uint8_t* sg) {
@@ -211,6 +223,7 @@ struct coop_sim {
   coop_ctx ctx(int k, int lane) {
     coop_ctx c;
     c.sm = sm.data() + lane; c.row = row; c.wmode = wmode; c.plans = g_coop_wmode == 1 ? K_COOP_PLANS_W : g_coop_wmode == 2 ? K_COOP_PLANS_H : K_COOP_PLANS;
+    c.kq = g_coop_wmode == 0 ? &K_KQ_TABLE[0][0] : nullptr;  // the default kernel's one-reduction xi variants; the other layouts keep the additions
     c.k = k; c.lane = lane; c.active = true; c.item = lane; c.n_pad = n_pad;
     c.lines = lines.data(); c.gslots = gslots.data(); c.fio = fio.data(); c.status = &status;
     return c;

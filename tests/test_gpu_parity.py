@@ -68,6 +68,26 @@ def test_fq_ptx_product_matches_portable_and_oracle(E):
     # x >= q is rejected like Fq::from_slice
     r, st = E.fq_op_batch(0, be(Q), be(1))
     assert st[0] == O.NOT_MEMBER
+    # 9 a +- b with one reduction (quotient estimate + table, fq.cuh fq_mul9_add): the routine sees Montgomery-form integers, so
+    # the operands are chosen there: sums that land on and around every multiple of q, the extremes, and random pairs
+    RINV = pow(1 << 256, -1, Q)
+    prng = random.Random(41)
+    pairs = [(0, 0), (Q - 1, Q - 1), (Q - 1, 0), (0, Q - 1), (1, Q - 9), (1, Q - 10)]
+    for k in range(1, 10):
+        for d in (-2, -1, 0, 1, 2):
+            t = k * Q + d
+            x = min(Q - 1, t // 9)
+            if 0 <= t - 9 * x < Q:
+                pairs.append((x, t - 9 * x))
+    pairs += [(prng.randrange(Q), prng.randrange(Q)) for _ in range(4096)]
+    xa = b"".join(be(x * RINV % Q) for x, _ in pairs)
+    za = b"".join(be(z * RINV % Q) for _, z in pairs)
+    plus, st = E.fq_op_batch(6, xa, za)
+    minus, st2 = E.fq_op_batch(7, xa, za)
+    assert not any(st) and not any(st2)
+    for i, (x, z) in enumerate(pairs):
+        assert plus[32 * i:32 * i + 32] == be((9 * x + z) % Q * RINV % Q), i
+        assert minus[32 * i:32 * i + 32] == be((9 * x - z) % Q * RINV % Q), i
 
 
 def test_fq12_ops(E):

@@ -374,3 +374,22 @@ def test_glv_decomposition_identity_and_bounds(hs):
         assert (v1 + v2 * lam - k) % R == 0, hex(k)
         worst = max(worst, abs(v1).bit_length(), abs(v2).bit_length())
     assert worst <= 128   # the magnitudes are returned in four limbs, so anything larger would already have failed the identity
+
+
+def test_mul9_add_one_reduction(hs):
+    """(9 x + z) mod q through the quotient estimate (fq.cuh fq_mul9_add, used for xi * x in the cooperative machine): exact
+    at every multiple of q the sum can cross, at the operand extremes, and on random operands."""
+    rng = random.Random(37)
+    cases = [(0, 0), (0, Q), (Q - 1, Q), (Q - 1, Q - 1), (Q - 1, 0), (1, Q - 9), (1, Q - 10), (0, Q - 1)]
+    for k in range(1, 10):                      # 9 x + z = k q + d for small d on both sides
+        for d in (-2, -1, 0, 1, 2):
+            t = k * Q + d
+            x = min(Q - 1, t // 9)
+            z = t - 9 * x
+            if 0 <= z <= Q:
+                cases.append((x, z))
+    cases += [(rng.randrange(Q), rng.randrange(Q + 1)) for _ in range(20000)]
+    out = buf(32)
+    for x, z in cases:
+        hs.hs_mul9_add(be(x), be(z), out)
+        assert int.from_bytes(out.raw, "big") == (9 * x + z) % Q, (hex(x), hex(z))
