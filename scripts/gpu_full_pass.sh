@@ -8,6 +8,6 @@ SMI=$!
 kill $SMI
 ( time timeout 600 python bench.py --impl reference --steps 2 --warmup 1 ) > gpurun_out/bench_ref.log 2>&1; tail -3 gpurun_out/bench_ref.log | cut -c1-400
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches_r01e.csv python bench.py --n 262144 --steps 2 --warmup 1 --cpu-sample 16 > gpurun_out/ncu_launch.log 2>&1
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"k_coop4_run|k_verify_lines" -c 2 -o gpurun_out/prof_r01_v7 python bench.py --n 131072 --steps 1 --warmup 1 --cpu-sample 16 > gpurun_out/ncu_prof_v7.log 2>&1
-tail -2 gpurun_out/ncu_prof_v7.log | cut -c1-300
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches_r01f.csv python bench.py --n 262144 --steps 2 --warmup 1 --cpu-sample 16 > gpurun_out/ncu_launch.log 2>&1
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"k_coop4_run|k_verify_lines" -c 2 -o gpurun_out/prof_r01_v8 python bench.py --n 131072 --steps 1 --warmup 1 --cpu-sample 16 > gpurun_out/ncu_prof_v8.log 2>&1
+tail -2 gpurun_out/ncu_prof_v8.log | cut -c1-300
