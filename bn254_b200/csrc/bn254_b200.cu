@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/bn254_b200.h"
@@ -580,7 +581,7 @@ __global__ void k_coop_gather(const u4* __restrict__ fio, size_t L, size_t block
 __global__ void __launch_bounds__(BN_BLOCK) k_rlc_prepare(g1aff* __restrict__ H, const uint8_t* __restrict__ hstatus,
                                                           const uint8_t* __restrict__ sigs, const uint8_t* __restrict__ pks,
                                                           const uint8_t* __restrict__ coeffs16, size_t n, int check_g2,
-                                                          uint8_t* __restrict__ sig_c, unsigned* __restrict__ bad) {
+                                                          uint8_t* __restrict__ sig_c, unsigned* __restrict__ bad, size_t L, size_t W) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int st = hstatus[i];
@@ -589,7 +590,63 @@ __global__ void __launch_bounds__(BN_BLOCK) k_rlc_prepare(g1aff* __restrict__ H,
     st = item_rlc_prepare(&hs, sig_c + 64 * i, &h, sigs + 64 * i, pks + 128 * i, coeffs16 + 16 * i, check_g2 != 0);
     if (!st) H[i] = hs;
   }
-  if (st) atomicOr(bad, 1u);
+  if (st) {
+    for (int k = 0; k < 64; k++) sig_c[64 * i + k] = 0;  // nothing of this item enters the slice's signature sum
+    atomicOr(bad + (i % L) / W, 1u);                     // its slice goes to the exact path
+  }
+}
+// The multi-pairing machine puts pair p on lane p % L (L lanes, stream p / L): slice s = lanes [s W, (s + 1) W) owns the items
+// { t L + s W + j : t < COOP_MULTI_K, j < W }.  One block per slice: the sum of its scaled signatures, affine.
+__global__ void __launch_bounds__(BN_BLOCK) k_rlc_slice_sums(const uint8_t* __restrict__ sig_c, size_t n, size_t L, size_t W,
+                                                             const unsigned* __restrict__ bad, uint8_t* __restrict__ agg) {
+  __shared__ jac<fq> sh[BN_BLOCK];
+  const size_t s = blockIdx.x;
+  jac<fq> acc;
+  pt_set_inf(&acc);
+  if (!bad[s]) {
+    for (size_t idx = threadIdx.x; idx < (size_t)COOP_MULTI_K * W; idx += BN_BLOCK) {
+      size_t lane = s * W + idx % W, p = (idx / W) * L + lane;
+      if (lane >= L || p >= n) continue;
+      jac<fq> q;
+      if (g1_from_raw(&q, sig_c + 64 * p) || pt_is_inf(&q)) continue;
+      pt_madd(&acc, &acc, &q.x, &q.y);
+    }
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int t = BN_BLOCK / 2; t > 0; t >>= 1) {
+    if (threadIdx.x < t) pt_add(&sh[threadIdx.x], &sh[threadIdx.x], &sh[threadIdx.x + t]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) g1_to_raw(agg + 64 * s, &sh[0]);
+}
+// verdict of slice s: prod of its groups' Miller partials * miller(sum of its scaled signatures, -G2), final exponentiation
+__global__ void __launch_bounds__(32) k_rlc_finish_slices(const fq12* __restrict__ partial, size_t groups, size_t gps,
+                                                          const uint8_t* __restrict__ agg, const unsigned* __restrict__ bad,
+                                                          const line_t* __restrict__ lines, uint8_t* __restrict__ verdict) {
+  if (threadIdx.x != 0) return;
+  const size_t s = blockIdx.x;
+  if (bad[s]) {
+    verdict[s] = ST_VERIFICATION_FAILED;
+    return;
+  }
+  fq12 acc, t;
+  fq12_set_one(&acc);
+  for (size_t g = s * gps; g < (s + 1) * gps && g < groups; g++) {
+    t = partial[g];
+    fq12_mul(&acc, &acc, &t);
+  }
+  g1j a;
+  if (g1_from_raw(&a, agg + 64 * s)) {
+    verdict[s] = ST_VERIFICATION_FAILED;
+    return;
+  }
+  if (!pt_is_inf(&a)) {
+    fq2 dummy = fq2_one();
+    miller_loop_2(&t, false, &a.x, &a.y, &dummy, &dummy, true, &a.x, &a.y, lines);
+    fq12_mul(&acc, &acc, &t);
+  }
+  verdict[s] = (uint8_t)item_final_exp_is_one(&acc);
 }
 
 // ---- point aggregation: strided mixed additions per thread, then a shared-memory tree per block
@@ -1379,38 +1436,90 @@ static int verify_rlc_dev_impl(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_l
                                const uint8_t* coeffs16, int flags, uint8_t* status, int* took_fast_path) {
   if (took_fast_path) *took_fast_path = 0;
   if (n == 0) return 0;
-  DALLOC(H, sizeof(g1aff) * n);
-  DALLOC(hst, n);
-  DALLOC(sigc, 64 * n);
-  DALLOC(bad, 4);
-  DALLOC(fbe, 384);
-  DALLOC(agg, 64);
-  DALLOC(st2, 4);
-  CK(cudaMemsetAsync(bad.p, 0, 4, ctx->stream));
-  int rc = hash_dev(ctx, msgs, msg_len, nullptr, n, H.as<g1aff>(), hst.as<uint8_t>(), nullptr);
-  if (rc) return rc;
-  LAUNCH(k_rlc_prepare, grid_for(n), BN_BLOCK, H.as<g1aff>(), hst.as<uint8_t>(), sigs, pks, coeffs16, n, (flags & 1) ? 0 : 1,
-         sigc.as<uint8_t>(), bad.as<unsigned>());
-  unsigned h_bad = 0;
-  D2H(&h_bad, bad.p, 4);
-  CK(cudaStreamSynchronize(ctx->stream));
-  if (!h_bad) {
-    // hst is all zero here (a hash error sets `bad`), H now holds c_i H(m_i)
-    rc = distinct_partial_points_dev(ctx, H.as<g1aff>(), hst.as<uint8_t>(), pks, n, fbe.as<uint8_t>(), st2.as<uint8_t>());
+  bool all_fast = true;
+  // chunks of 2^20 triples (the line sets of a chunk take 26 GB); a chunk is cut into up to 64 slices of whole multi-pairing
+  // groups, every slice gets its own verdict from the one pass, and only failing slices are redone by the exact path
+  const size_t CH = (size_t)1 << 20, per_group = (size_t)COOP_LANES * COOP_MULTI_K;
+  const size_t cap = n < CH ? n : CH, cap_groups = (cap + per_group - 1) / per_group, capL = cap_groups * COOP_LANES;
+  DALLOC(H, sizeof(g1aff) * cap);
+  DALLOC(hst, cap);
+  DALLOC(sigc, 64 * cap);
+  DALLOC(bad, 4 * 64);
+  DALLOC(agg, 64 * 64);
+  DALLOC(verdict, 64);
+  DALLOC(err, 8);
+  DALLOC(LN, sizeof(u4) * COOP_MULTI_K * COOP_LINE_FQ * 2 * K_N_LINES * capL);
+  DALLOC(FIO, sizeof(u4) * 6 * 2 * 2 * capL);
+  DALLOC(partial, sizeof(fq12) * cap_groups);
+  for (size_t off = 0; off < n; off += CH) {
+    const size_t m = n - off < CH ? n - off : CH;
+    const size_t groups = (m + per_group - 1) / per_group, L = groups * COOP_LANES;
+    const size_t S = groups < 64 ? groups : 64, gps = (groups + S - 1) / S, W = gps * COOP_LANES;
+    const size_t slices = (groups + gps - 1) / gps;
+    const uint8_t *cm = msgs + msg_len * off, *cs = sigs + 64 * off, *cp = pks + 128 * off;
+    CK(cudaMemsetAsync(bad.p, 0, 4 * 64, ctx->stream));
+    CK(cudaMemsetAsync(err.p, 0xff, 8, ctx->stream));
+    int rc = hash_dev(ctx, cm, msg_len, nullptr, m, H.as<g1aff>(), hst.as<uint8_t>(), nullptr);
     if (rc) return rc;
-    rc = sum_dev_impl<fq>(ctx, sigc.as<uint8_t>(), nullptr, n, agg.as<uint8_t>(), st2.as<uint8_t>() + 1);
+    LAUNCH(k_rlc_prepare, grid_for(m), BN_BLOCK, H.as<g1aff>(), hst.as<uint8_t>(), cs, cp, coeffs16 + 16 * off, m, (flags & 1) ? 0 : 1,
+           sigc.as<uint8_t>(), bad.as<unsigned>(), L, W);
+    // pairs of items that cannot ride are harmless here (skipped or multiplied into a slice that is already marked)
+    LAUNCH(k_pair_lines, grid_for(L * COOP_MULTI_K), BN_BLOCK, H.as<g1aff>(), hst.as<uint8_t>(), cp, m, L, LN.as<u4>(),
+           err.as<unsigned long long>(), (size_t)0);
+    rc = launch_coop_groups(ctx, 4, L, L, LN.as<u4>(), (u4*)nullptr, FIO.as<u4>(), (uint8_t*)nullptr, groups);
     if (rc) return rc;
-    LAUNCH(k_distinct_finish, 1, 32, fbe.as<uint8_t>(), 1, agg.as<uint8_t>(), ctx->d_lines, st2.as<uint8_t>() + 2);
-    uint8_t h_st[4] = {1, 1, 1, 1};
-    D2H(h_st, st2.p, 3);
+    LAUNCH(k_coop_gather, grid_for(groups), BN_BLOCK, FIO.as<u4>(), L, groups, partial.as<fq12>());
+    LAUNCH(k_rlc_slice_sums, (unsigned)slices, BN_BLOCK, sigc.as<uint8_t>(), m, L, W, bad.as<unsigned>(), agg.as<uint8_t>());
+    LAUNCH(k_rlc_finish_slices, (unsigned)slices, 32, partial.as<fq12>(), groups, gps, agg.as<uint8_t>(), bad.as<unsigned>(), ctx->d_lines,
+           verdict.as<uint8_t>());
+    uint8_t h_v[64];
+    D2H(h_v, verdict.p, slices);
     CK(cudaStreamSynchronize(ctx->stream));
-    if (h_st[0] == 0 && h_st[1] == 0 && h_st[2] == 0) {
-      CK(cudaMemsetAsync(status, 0, n, ctx->stream));
-      if (took_fast_path) *took_fast_path = 1;
-      return 0;
+    // the items of a slice are COOP_MULTI_K runs of W consecutive triples; passing runs get status 0, failing runs are packed
+    // into one contiguous batch for a single exact pass (a failing slice alone would fill a fraction of the GPU)
+    std::vector<std::pair<size_t, size_t>> redo;
+    size_t redo_items = 0;
+    for (size_t sl = 0; sl < slices; sl++) {
+      for (size_t t = 0; t < COOP_MULTI_K; t++) {
+        size_t lo = t * L + sl * W, hi = lo + W;
+        if (lo >= m) break;
+        if (hi > m) hi = m;
+        if (hi > (t + 1) * L) hi = (t + 1) * L;
+        if (hi <= lo) continue;
+        if (h_v[sl] == 0) {
+          CK(cudaMemsetAsync(status + off + lo, 0, hi - lo, ctx->stream));
+        } else {
+          redo.push_back({lo, hi});
+          redo_items += hi - lo;
+        }
+      }
+    }
+    if (redo_items) {
+      all_fast = false;
+      DALLOC(pm, msg_len * redo_items);
+      DALLOC(ps, 64 * redo_items);
+      DALLOC(pp, 128 * redo_items);
+      DALLOC(pst, redo_items);
+      size_t at = 0;
+      for (auto& r : redo) {
+        size_t c = r.second - r.first;
+        if (msg_len) CK(cudaMemcpyAsync(pm.as<uint8_t>() + msg_len * at, cm + msg_len * r.first, msg_len * c, cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ps.as<uint8_t>() + 64 * at, cs + 64 * r.first, 64 * c, cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(pp.as<uint8_t>() + 128 * at, cp + 128 * r.first, 128 * c, cudaMemcpyDeviceToDevice, ctx->stream));
+        at += c;
+      }
+      rc = verify_dev_impl(ctx, pm.as<uint8_t>(), msg_len, ps.as<uint8_t>(), pp.as<uint8_t>(), redo_items, pst.as<uint8_t>());
+      if (rc) return rc;
+      at = 0;
+      for (auto& r : redo) {
+        size_t c = r.second - r.first;
+        CK(cudaMemcpyAsync(status + off + r.first, pst.as<uint8_t>() + at, c, cudaMemcpyDeviceToDevice, ctx->stream));
+        at += c;
+      }
     }
   }
-  return verify_dev_impl(ctx, msgs, msg_len, sigs, pks, n, status);
+  if (took_fast_path) *took_fast_path = all_fast ? 1 : 0;
+  return 0;
 }
 
 extern "C" {

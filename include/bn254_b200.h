@@ -95,9 +95,11 @@ int bn254_verify_batch_dev(bn254_ctx*, const uint8_t* msgs, size_t msg_len, cons
  * triples are accepted together iff  prod_i e(c_i H(msg_i), pk_i) * e(sum_i c_i sig_i, -G2) == 1  for 128-bit coefficients
  * c_i (coeffs16: n x 16 bytes, secret from whoever produced the signatures; NULL in the host-buffer form = drawn from
  * /dev/urandom; the bytes are read as two 64-bit halves and c_i = lo + hi * lambda mod r, lambda the GLV eigenvalue, which
- * keeps 2^128 distinct coefficients and halves the scalar multiplications).  One shared final exponentiation instead of n.  If every item decodes, every pk is in G2 and the
- * combined check passes, all statuses are 0 (what verify_batch returns, up to a 2^-128 false-accept probability) and
- * *took_fast_path = 1; in every other case the exact per-item path runs and status[] is exactly verify_batch's.
+ * keeps 2^128 distinct coefficients and halves the scalar multiplications).  One pass gives a verdict per SLICE (a 2^20-triple
+ * chunk is cut into up to 64 slices of whole multi-pairing groups, each with its own product, signature sum and final
+ * exponentiation): triples of a passing slice get status 0 (what verify_batch returns, up to a 2^-128 false-accept
+ * probability); slices that fail, or hold an item that does not decode or a pk outside G2, are packed together and redone by
+ * the exact per-item path, so status[] is always verify_batch's.  *took_fast_path = 1 iff no slice had to be redone.
  * flags bit 0: the caller vouches that every pk is in the r-torsion (e.g. it came from from_compressed) -- skips that test. */
 int bn254_verify_batch_rlc(bn254_ctx*, const uint8_t* msgs, size_t msg_len, const uint8_t* sigs, const uint8_t* pks, size_t n,
                            const uint8_t* coeffs16, int flags, uint8_t* status, int* took_fast_path);

@@ -602,3 +602,28 @@ def test_verify_batch_rlc(E):
     st, fast = E.verify_batch_rlc(msgs, 32, sigs, bytes(p6), coeffs)
     assert not fast and st == O.verify_batch(msgs, 32, sigs, bytes(p6), n, NTHREADS) == E.verify_batch(msgs, 32, sigs, bytes(p6))
     assert E.verify_batch_rlc(b"", 32, b"", b"") == (b"", False)
+
+
+def test_verify_batch_rlc_slices_isolate_failures(E):
+    """The randomised pass gives one verdict per slice of whole multi-pairing groups (up to 64 per 2^20-triple chunk); only
+    failing slices are redone by the exact path.  20 000 triples with forged, undecodable and out-of-subgroup items spread over
+    several slices: the statuses are exactly verify_batch's."""
+    import edge_points
+    n = 20000
+    msgs, sks, sigs, pks = _signed_set(E, n, seed=63)
+    coeffs = synth.rand_bytes(4321, 16 * n)
+    st, fast = E.verify_batch_rlc(msgs, 32, sigs, pks, coeffs)
+    assert fast and st == bytes(n)
+    s2, p2 = bytearray(sigs), bytearray(pks)
+    for i in (3, 777, 9999, 19999):
+        s2[64 * i:64 * i + 64] = O.g1_neg(sigs[64 * i:64 * i + 64])[1]
+    s2[64 * 5000 + 63] ^= 1                                                       # undecodable signature
+    p2[128 * 15000:128 * 15001] = [pt for pt, inside in edge_points.subgroup_edge_points() if not inside][0]   # key outside G2
+    s2[64 * 12345:64 * 12346] = bytes(64)                                         # infinite signature, real key: rejected
+    s2, p2 = bytes(s2), bytes(p2)
+    st, fast = E.verify_batch_rlc(msgs, 32, s2, p2, coeffs)
+    want = E.verify_batch(msgs, 32, s2, p2)
+    assert not fast and st == want
+    bad = {i for i in range(n) if want[i]}
+    assert bad == {3, 777, 5000, 9999, 12345, 15000, 19999}
+    assert want == O.verify_batch(msgs, 32, s2, p2, n, NTHREADS)
