@@ -249,8 +249,8 @@ def run_engine(args):
         tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
         traffic = tj["k_coop4_run"]["dram_bytes_per_launch"]
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
-        launch_ms = coop_ms / max(1, (n + (1 << 17) - 1) >> 17)
-        items = min(n, 1 << 17)
+        launch_ms = coop_ms / max(1, (n + (1 << 20) - 1) >> 20)
+        items = min(n, 1 << 20)
         hbm = {"achieved_gbs": traffic * items / tj["k_coop4_run"]["items_per_launch"] / (launch_ms * 1e-3) / 1e9,
                "peak_gbs": peaks.get("hbm_gbs", 6650.0), "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"}
         hbm["frac"] = hbm["achieved_gbs"] / hbm["peak_gbs"]
@@ -279,8 +279,8 @@ def run_engine(args):
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
         "data": "synthetic",
         "config": {"workload": "batch verify 2^20 independent (32-byte msg, sig, pk) triples per GPU (BASELINE configs[1])",
-                   "triples_per_gpu": n, "msg_len": 32, "l2": "inputs+workspace (%.0f MB) larger than L2" % ((224 + 448) * n / 1e6),
-                   "pairings_per_sec": value * 2, "pairing_kernels": "cooperative machine: six warps per 32-item group, four groups per block (one per SM sub-partition), chunks of 2^17"},
+                   "triples_per_gpu": n, "msg_len": 32, "l2": "inputs + line-set workspace (%.1f GB, written and read once per step) larger than L2" % ((224 + 50112 + 2304) * n / 1e9),
+                   "pairings_per_sec": value * 2, "pairing_kernels": "cooperative machine: six warps per 32-item group, four groups per block (one per SM sub-partition), workspace chunks of 2^20 items"},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 224 * n, "d2h_bytes_per_step": n, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches, "clocks": sampler.result(), "roofline": roof,
         "cpu_baseline": cpu_line,

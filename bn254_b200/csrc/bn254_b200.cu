@@ -324,6 +324,9 @@ __global__ void __launch_bounds__(BN_BLOCK, BN_LINES_MINB) k_verify_lines(const 
 #ifndef BN_COOP_STAGGER
 #define BN_COOP_STAGGER 0
 #endif
+#ifndef BN_COOP_CHUNK_LOG2
+#define BN_COOP_CHUNK_LOG2 20
+#endif
 #ifndef BN_COOP_DEFAULT_GROUPS4
 #define BN_COOP_DEFAULT_GROUPS4 1
 #endif
@@ -817,6 +820,7 @@ struct bn254_ctx {
   // 3: cooperative, warp-local layout (six lanes per item)
   int pairing_mode = 0;
   unsigned coop_stagger = BN_COOP_STAGGER;  // start offset between co-resident blocks of k_coop_run, SM cycles
+  int chunk_log2 = BN_COOP_CHUNK_LOG2;  // verify: items per line-set workspace chunk (50 KB of line sets per item)
   int coop_groups4 = BN_COOP_DEFAULT_GROUPS4;  // block layout: four groups per 24-warp block, one group per sub-partition (k_coop4_run)
   bool coop_h = BN_COOP_DEFAULT_H;  // verify uses the half-warp layout (k_cooph_run, pairing mode 4)
   bool coop_w = BN_COOP_DEFAULT_W;  // layout mode 0 uses for verify (BN254_COOP_W=0/1 in the environment overrides)
@@ -870,6 +874,10 @@ int bn254_ctx_create(int device, bn254_ctx** out) {
   bn254_ctx* ctx = new bn254_ctx();
   ctx->device = device;
   if (const char* w = getenv("BN254_COOP_W")) ctx->coop_w = w[0] == '1';
+  if (const char* w = getenv("BN254_COOP_CHUNK_LOG2")) {
+    int v = atoi(w);
+    if (v >= 10 && v <= 21) ctx->chunk_log2 = v;
+  }
   if (const char* w = getenv("BN254_COOP_H")) ctx->coop_h = w[0] == '1';
   if (const char* w = getenv("BN254_COOP_GROUPS4")) ctx->coop_groups4 = atoi(w);
   if (const char* w = getenv("BN254_COOP_STAGGER")) ctx->coop_stagger = (unsigned)atoi(w);  // tuning knob (cycles)
@@ -1087,9 +1095,10 @@ static int verify_dev_impl(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, 
   const bool coop = ctx->pairing_mode != 1;
   const bool wl = ctx->pairing_mode == 3 || (ctx->pairing_mode == 0 && ctx->coop_w);
   const bool hl = !wl && (ctx->pairing_mode == 4 || (ctx->pairing_mode == 0 && ctx->coop_h));
-  // chunking bounds the workspace: the cooperative path stores 174 line sets (50 KB) per item
+  // chunking bounds the workspace: the cooperative path stores 174 line sets (50 KB) per item, 55 GB for the default chunk of
+  // 2^20 items (of the 180 GB; BN254_COOP_CHUNK_LOG2 lowers it: 2^17-item chunks cost 1.1 % of the throughput)
   // (warp-local layout: a whole number of waves of 30-item blocks, so that the last wave of a chunk is not mostly empty)
-  const size_t CHUNK = !coop ? ((size_t)1 << 20) : wl ? (size_t)ctx->sm_count * BN_COOP_MINB * COOPW_ITEMS * 7 : ((size_t)1 << 17);
+  const size_t CHUNK = !coop ? ((size_t)1 << 20) : wl ? (size_t)ctx->sm_count * BN_COOP_MINB * COOPW_ITEMS * 7 : ((size_t)1 << ctx->chunk_log2);
   size_t cap = n < CHUNK ? n : CHUNK;
   size_t cap_pad = (cap + COOP_LANES - 1) / COOP_LANES * COOP_LANES;
   // the hash runs once over the whole batch: its compacting rounds are latency-bound when a round gets small, so one
