@@ -627,3 +627,33 @@ def test_verify_batch_rlc_slices_isolate_failures(E):
     bad = {i for i in range(n) if want[i]}
     assert bad == {3, 777, 5000, 9999, 12345, 15000, 19999}
     assert want == O.verify_batch(msgs, 32, s2, p2, n, NTHREADS)
+
+
+def test_verify_workspace_chunking(E):
+    """verify_batch walks the batch in workspace chunks (2^20 items by default, BN254_COOP_CHUNK_LOG2): with 2^12-item chunks a
+    10 000-triple batch takes three passes (the hash runs once over the whole batch, line sets and the machine per chunk) and
+    must give the same verdicts as the single-chunk context, invalid items on both sides of the chunk borders included."""
+    from bn254_b200._native import Context
+    n = 10000
+    msgs, sks, sigs, pks = _signed_set(E, n, seed=71)
+    sigs = bytearray(sigs)
+    for i in (0, 4095, 4096, 4097, 8191, 8192, 9999):
+        sigs[64 * i:64 * i + 64] = O.g1_neg(bytes(sigs[64 * i:64 * i + 64]))[1]
+    sigs = bytes(sigs)
+    want = E.verify_batch(msgs, 32, sigs, pks)
+    assert {i for i in range(n) if want[i]} == {0, 4095, 4096, 4097, 8191, 8192, 9999}
+    old = os.environ.get("BN254_COOP_CHUNK_LOG2")
+    os.environ["BN254_COOP_CHUNK_LOG2"] = "12"
+    try:
+        small = Context(0)
+    finally:
+        if old is None:
+            del os.environ["BN254_COOP_CHUNK_LOG2"]
+        else:
+            os.environ["BN254_COOP_CHUNK_LOG2"] = old
+    try:
+        assert E.verify_batch(msgs, 32, sigs, pks, ctx=small) == want
+        st, fast = E.verify_batch_rlc(msgs, 32, sigs, pks, synth.rand_bytes(5, 16 * n), ctx=small)
+        assert not fast and st == want
+    finally:
+        small.close()
