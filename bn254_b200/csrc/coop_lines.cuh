@@ -54,7 +54,7 @@ struct lines_consts {
   fq2 v[4];
 };
 
-BN_FN void coop_emit_scaled_v(u4* lines, size_t set, size_t n_pad, size_t item, bool use, const fq2& ell_0, const fq2& ell_vw, const fq2& ell_vv,
+BN_NOINLINE void coop_emit_scaled_v(u4* lines, size_t set, size_t n_pad, size_t item, bool use, const fq2& ell_0, const fq2& ell_vw, const fq2& ell_vv,
                               const fq2& pxy) {
   fq2 l0, l3, l4;
   if (use) {
