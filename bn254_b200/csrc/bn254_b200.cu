@@ -221,6 +221,8 @@ __global__ void __launch_bounds__(BN_BLOCK) k_fq_op(int op, const uint8_t* __res
     else if (op == 5) r = fq_mul_portable(x, y);
     else if (op == 6) r = fq_mul9_add(x, y, &K_KQ_TABLE[0][0]);              // 9 x + y
     else if (op == 7) r = fq_mul9_add(x, fq_q_minus(y), &K_KQ_TABLE[0][0]);  // 9 x - y
+    else if (op == 8) r = fq_3t_2z(x, y, &K_KQ_TABLE[0][0]);                 // 3 x + 2 y
+    else if (op == 9) r = fq_3t_2z(x, fq_q_minus(y), &K_KQ_TABLE[0][0]);     // 3 x - 2 y
     else st = ST_INVALID_ENCODING;
   }
   status[i] = (uint8_t)st;

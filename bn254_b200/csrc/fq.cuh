@@ -206,12 +206,42 @@ BN_FN fq fq_csub(const fq& a) {
 #endif
 BN_FN fq fq_neg(const fq& a) { return fq_sub(fq_zero(), a); }
 
+#define BN_KQ_RECIP 0xa948e8c0u /* floor(2^59 / ((q >> 226) + 1)) */
+// t (nine limbs, below 11 q) mod q: quotient estimate from the top bits, k q from the table, one conditional subtraction
+BN_FN fq fq_reduce9(const uint32_t (&t)[9], const uint32_t* kq) {
+  fq r;
+#if defined(__CUDA_ARCH__)
+  const uint32_t k = min(__umulhi(__funnelshift_r(t[7], t[8], 2), BN_KQ_RECIP) >> 27, 10u);
+  const uint4 e0 = *(const uint4*)(kq + 8 * k), e1 = *(const uint4*)(kq + 8 * k + 4);
+  asm("sub.cc.u32 %0, %8, %16;\n\t"
+      "subc.cc.u32 %1, %9, %17;\n\t"
+      "subc.cc.u32 %2, %10, %18;\n\t"
+      "subc.cc.u32 %3, %11, %19;\n\t"
+      "subc.cc.u32 %4, %12, %20;\n\t"
+      "subc.cc.u32 %5, %13, %21;\n\t"
+      "subc.cc.u32 %6, %14, %22;\n\t"
+      "subc.u32 %7, %15, %23;\n\t"
+      : "=&r"(r.l[0]), "=&r"(r.l[1]), "=&r"(r.l[2]), "=&r"(r.l[3]), "=&r"(r.l[4]), "=&r"(r.l[5]), "=&r"(r.l[6]), "=&r"(r.l[7])
+      : "r"(t[0]), "r"(t[1]), "r"(t[2]), "r"(t[3]), "r"(t[4]), "r"(t[5]), "r"(t[6]), "r"(t[7]), "r"(e0.x), "r"(e0.y), "r"(e0.z),
+        "r"(e0.w), "r"(e1.x), "r"(e1.y), "r"(e1.z), "r"(e1.w));
+#else
+  const uint32_t T = (t[8] << 30) | (t[7] >> 2);
+  uint32_t k = (uint32_t)(((uint64_t)T * BN_KQ_RECIP) >> 32) >> 27;
+  if (k > 10) k = 10;
+  uint32_t bw = 0;
+  for (int i = 0; i < 8; i++) {
+    uint64_t d = (uint64_t)t[i] - kq[8 * k + i] - bw;
+    r.l[i] = (uint32_t)d;
+    bw = (uint32_t)(d >> 63);
+  }
+#endif
+  return fq_csub(r);
+}
 // (9 x + z) mod q in one reduction, for x < q and z <= q (canonical, or q itself): t = 9 x + z < 10 q is formed on nine
 // limbs, the quotient k = floor(t / q) is estimated from the top 32 bits of t >> 226 (reciprocal multiplication; the
 // estimate is k or k - 1, checked exhaustively at the multiples of q and on 3 * 10^5 random values in the tests), k q comes
 // from a table (kq: entries of 8 limbs, k q mod 2^256, k = 0..10) and one conditional subtraction finishes.  Replaces the
 // five modular additions of 8 x + x + z; xi x = (9 x0 - x1, 9 x1 + x0) is two of these (coop.cuh coop_put_p).
-#define BN_KQ_RECIP 0xa948e8c0u /* floor(2^59 / ((q >> 226) + 1)) */
 BN_FN fq fq_mul9_add(const fq& x, const fq& z, const uint32_t* kq) {
   uint32_t t[9];
 #if defined(__CUDA_ARCH__)
@@ -243,22 +273,7 @@ BN_FN fq fq_mul9_add(const fq& x, const fq& z, const uint32_t* kq) {
       "addc.u32 %8, %8, 0;\n\t"
       : "+r"(t[0]), "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]), "+r"(t[8])
       : "r"(z.l[0]), "r"(z.l[1]), "r"(z.l[2]), "r"(z.l[3]), "r"(z.l[4]), "r"(z.l[5]), "r"(z.l[6]), "r"(z.l[7]));
-  // (items whose inputs failed validation flow through the machine with arbitrary bits: the clamp keeps the index inside the table)
-  const uint32_t k = min(__umulhi(__funnelshift_r(t[7], t[8], 2), BN_KQ_RECIP) >> 27, 10u);
-  const uint4 e0 = *(const uint4*)(kq + 8 * k), e1 = *(const uint4*)(kq + 8 * k + 4);
-  fq r;
-  asm("sub.cc.u32 %0, %8, %16;\n\t"
-      "subc.cc.u32 %1, %9, %17;\n\t"
-      "subc.cc.u32 %2, %10, %18;\n\t"
-      "subc.cc.u32 %3, %11, %19;\n\t"
-      "subc.cc.u32 %4, %12, %20;\n\t"
-      "subc.cc.u32 %5, %13, %21;\n\t"
-      "subc.cc.u32 %6, %14, %22;\n\t"
-      "subc.u32 %7, %15, %23;\n\t"
-      : "=&r"(r.l[0]), "=&r"(r.l[1]), "=&r"(r.l[2]), "=&r"(r.l[3]), "=&r"(r.l[4]), "=&r"(r.l[5]), "=&r"(r.l[6]), "=&r"(r.l[7])
-      : "r"(t[0]), "r"(t[1]), "r"(t[2]), "r"(t[3]), "r"(t[4]), "r"(t[5]), "r"(t[6]), "r"(t[7]), "r"(e0.x), "r"(e0.y), "r"(e0.z),
-        "r"(e0.w), "r"(e1.x), "r"(e1.y), "r"(e1.z), "r"(e1.w));
-  return fq_csub(r);
+  return fq_reduce9(t, kq);  // (the clamp inside keeps the table index in range for items that carry arbitrary bits)
 #else
   uint64_t c = 0;
   for (int i = 0; i < 9; i++) {
@@ -267,18 +282,57 @@ BN_FN fq fq_mul9_add(const fq& x, const fq& z, const uint32_t* kq) {
     t[i] = (uint32_t)c;
     c >>= 32;
   }
-  const uint32_t T = (t[8] << 30) | (t[7] >> 2);
-  uint32_t k = (uint32_t)(((uint64_t)T * BN_KQ_RECIP) >> 32) >> 27;
-  if (k > 10) k = 10;
-  fq r;
-  uint32_t bw = 0;
-  for (int i = 0; i < 8; i++) {
-    uint64_t d = (uint64_t)t[i] - kq[8 * k + i] - bw;
-    r.l[i] = (uint32_t)d;
-    bw = (uint32_t)(d >> 63);
-  }
-  return fq_csub(r);
+  return fq_reduce9(t, kq);
 #endif
+}
+// (3 t + 2 z) mod q for t < q, z <= q, with one reduction: the tail of the Granger-Scott squaring, 3 t +- 2 a, is this with
+// z = a or z = q - a (coop.cuh coop_commit)
+BN_FN fq fq_3t_2z(const fq& t, const fq& z, const uint32_t* kq) {
+  uint32_t v[9];
+#if defined(__CUDA_ARCH__)
+  uint32_t s[9], w[9];
+  s[0] = t.l[0] << 1;
+  w[0] = z.l[0] << 1;
+#pragma unroll
+  for (int i = 1; i < 8; i++) {
+    s[i] = __funnelshift_l(t.l[i - 1], t.l[i], 1);
+    w[i] = __funnelshift_l(z.l[i - 1], z.l[i], 1);
+  }
+  s[8] = t.l[7] >> 31;
+  w[8] = z.l[7] >> 31;
+  asm("add.cc.u32 %0, %9, %18;\n\t"
+      "addc.cc.u32 %1, %10, %19;\n\t"
+      "addc.cc.u32 %2, %11, %20;\n\t"
+      "addc.cc.u32 %3, %12, %21;\n\t"
+      "addc.cc.u32 %4, %13, %22;\n\t"
+      "addc.cc.u32 %5, %14, %23;\n\t"
+      "addc.cc.u32 %6, %15, %24;\n\t"
+      "addc.cc.u32 %7, %16, %25;\n\t"
+      "addc.u32 %8, %17, 0;\n\t"
+      : "=&r"(v[0]), "=&r"(v[1]), "=&r"(v[2]), "=&r"(v[3]), "=&r"(v[4]), "=&r"(v[5]), "=&r"(v[6]), "=&r"(v[7]), "=&r"(v[8])
+      : "r"(s[0]), "r"(s[1]), "r"(s[2]), "r"(s[3]), "r"(s[4]), "r"(s[5]), "r"(s[6]), "r"(s[7]), "r"(s[8]), "r"(t.l[0]), "r"(t.l[1]),
+        "r"(t.l[2]), "r"(t.l[3]), "r"(t.l[4]), "r"(t.l[5]), "r"(t.l[6]), "r"(t.l[7]));
+  asm("add.cc.u32 %0, %0, %9;\n\t"
+      "addc.cc.u32 %1, %1, %10;\n\t"
+      "addc.cc.u32 %2, %2, %11;\n\t"
+      "addc.cc.u32 %3, %3, %12;\n\t"
+      "addc.cc.u32 %4, %4, %13;\n\t"
+      "addc.cc.u32 %5, %5, %14;\n\t"
+      "addc.cc.u32 %6, %6, %15;\n\t"
+      "addc.cc.u32 %7, %7, %16;\n\t"
+      "addc.u32 %8, %8, %17;\n\t"
+      : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8])
+      : "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]), "r"(w[8]));
+#else
+  uint64_t c = 0;
+  for (int i = 0; i < 9; i++) {
+    uint64_t ti = i < 8 ? t.l[i] : 0, zi = i < 8 ? z.l[i] : 0;
+    c += 3 * ti + 2 * zi;
+    v[i] = (uint32_t)c;
+    c >>= 32;
+  }
+#endif
+  return fq_reduce9(v, kq);
 }
 // q - a as a plain integer (a <= q - 1 gives 1..q; a == 0 gives q itself, which fq_mul9_add accepts as its z)
 BN_FN fq fq_q_minus(const fq& a) {

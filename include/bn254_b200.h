@@ -155,7 +155,8 @@ int bn254_finish_distinct(bn254_ctx*, const uint8_t* partials384, size_t n_parti
 int bn254_miller_loop_batch(bn254_ctx*, const uint8_t* g1s, const uint8_t* g2s, size_t k, size_t n, uint8_t* f_out384, uint8_t* status);
 int bn254_final_exp_batch(bn254_ctx*, const uint8_t* f_in384, size_t n, uint8_t* gt_out384, uint8_t* status);
 /* Fq self-test hook: op 0 mul, 1 add, 2 sub, 3 inv, 4 sqrt (status 6 for a non-residue), 5 mul (portable cross-check variant),
- * 6 / 7: 9 a + b / 9 a - b through the one-reduction routine the cooperative machine uses for xi * x */
+ * 6 / 7: 9 a + b / 9 a - b, 8 / 9: 3 a + 2 b / 3 a - 2 b through the one-reduction routines the cooperative machine uses for
+ * xi * x and for the tail of the cyclotomic squaring */
 int bn254_fq_op_batch(bn254_ctx*, int op, const uint8_t* a32, const uint8_t* b32, size_t n, uint8_t* out32, uint8_t* status);
 /* Fq12 self-test hook: op 0 mul, 1 sqr, 2 inv, 3 cyclotomic sqr, 4..6 frobenius 1..3, 7 conj */
 int bn254_fq12_op_batch(bn254_ctx*, int op, const uint8_t* a384, const uint8_t* b384, size_t n, uint8_t* out384, uint8_t* status);

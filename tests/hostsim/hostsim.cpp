@@ -179,6 +179,18 @@ API void hs_mul9_add(const uint8_t* x_be, const uint8_t* z_be, uint8_t* out_be) 
   }
 }
 
+// (3 t + 2 z) mod q with one reduction (fq.cuh fq_3t_2z); z may equal q
+API void hs_3t_2z(const uint8_t* t_be, const uint8_t* z_be, uint8_t* out_be) {
+  fq t, z;
+  u256_from_be(t.l, t_be);
+  u256_from_be(z.l, z_be);
+  fq r = fq_3t_2z(t, z, &K_KQ_TABLE[0][0]);
+  for (int i = 0; i < 8; i++) {
+    uint32_t w = r.l[7 - i];
+    out_be[4 * i] = (uint8_t)(w >> 24); out_be[4 * i + 1] = (uint8_t)(w >> 16); out_be[4 * i + 2] = (uint8_t)(w >> 8); out_be[4 * i + 3] = (uint8_t)w;
+  }
+}
+
 // GLV decomposition used by signing: k (32 bytes big-endian, any value; reduced mod r first like Fr::from_slice) ->
 // |k1|, |k2| as 4 little-endian u32 limbs each, signs in sg[0], sg[1]
 API void hs_glv_decompose(const uint8_t* k_be, uint32_t* k1, uint32_t* k2, uint8_t* sg) {

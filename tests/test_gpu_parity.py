@@ -88,6 +88,20 @@ def test_fq_ptx_product_matches_portable_and_oracle(E):
     for i, (x, z) in enumerate(pairs):
         assert plus[32 * i:32 * i + 32] == be((9 * x + z) % Q * RINV % Q), i
         assert minus[32 * i:32 * i + 32] == be((9 * x - z) % Q * RINV % Q), i
+    for k in range(1, 5):                       # 3 t + 2 z = k q + d for the tail of the cyclotomic squaring
+        for d in (-2, -1, 0, 1, 2):
+            v = k * Q + d
+            t = min(Q - 1, v // 3)
+            if (v - 3 * t) % 2 == 0 and 0 <= (v - 3 * t) // 2 < Q:
+                pairs.append((t, (v - 3 * t) // 2))
+    xa = b"".join(be(x * RINV % Q) for x, _ in pairs)
+    za = b"".join(be(z * RINV % Q) for _, z in pairs)
+    plus, st = E.fq_op_batch(8, xa, za)
+    minus, st2 = E.fq_op_batch(9, xa, za)
+    assert not any(st) and not any(st2)
+    for i, (x, z) in enumerate(pairs):
+        assert plus[32 * i:32 * i + 32] == be((3 * x + 2 * z) % Q * RINV % Q), i
+        assert minus[32 * i:32 * i + 32] == be((3 * x - 2 * z) % Q * RINV % Q), i
 
 
 def test_fq12_ops(E):

@@ -393,3 +393,14 @@ def test_mul9_add_one_reduction(hs):
     for x, z in cases:
         hs.hs_mul9_add(be(x), be(z), out)
         assert int.from_bytes(out.raw, "big") == (9 * x + z) % Q, (hex(x), hex(z))
+    cases2 = [(0, 0), (0, Q), (Q - 1, Q), (Q - 1, Q - 1), (Q - 1, 0)]
+    for k in range(1, 5):                       # 3 t + 2 z = k q + d
+        for d in (-2, -1, 0, 1, 2):
+            v = k * Q + d
+            for t in (min(Q - 1, v // 3), max(0, (v - 2 * Q + 2) // 3)):
+                if (v - 3 * t) % 2 == 0 and 0 <= (v - 3 * t) // 2 <= Q and 0 <= t < Q:
+                    cases2.append((t, (v - 3 * t) // 2))
+    cases2 += [(rng.randrange(Q), rng.randrange(Q + 1)) for _ in range(20000)]
+    for t, z in cases2:
+        hs.hs_3t_2z(be(t), be(z), out)
+        assert int.from_bytes(out.raw, "big") == (3 * t + 2 * z) % Q, (hex(t), hex(z))
