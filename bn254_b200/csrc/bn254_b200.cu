@@ -813,6 +813,8 @@ struct bn254_ctx {
   int device = 0;
   int sm_count = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // host-buffer verify: signatures and keys are uploaded here while the hash kernels run
+  cudaEvent_t ev_alloc = nullptr, ev_copy = nullptr;
   line_t* d_lines = nullptr;
   aff<fq>* d_comb_g1 = nullptr;   // (d + 1) * 16^w * G1 generator
   aff<fq2>* d_comb_g2 = nullptr;  // (d + 1) * 16^w * G2 generator
@@ -894,6 +896,9 @@ int bn254_ctx_create(int device, bn254_ctx** out) {
   ctx->sm_count = prop.multiProcessorCount;
   if ((e = cudaDeviceSetLimit(cudaLimitStackSize, 16 * 1024)) != cudaSuccess) return fail("cudaDeviceSetLimit(stack)", e);
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+  if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate(copy)", e);
+  if ((e = cudaEventCreateWithFlags(&ctx->ev_alloc, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+  if ((e = cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
   cudaMemPool_t pool;
   if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
     uint64_t thr = UINT64_MAX;
@@ -928,6 +933,12 @@ void bn254_ctx_destroy(bn254_ctx* ctx) {
   if (ctx->d_lines) cudaFree(ctx->d_lines);
   if (ctx->d_comb_g1) cudaFree(ctx->d_comb_g1);
   if (ctx->d_comb_g2) cudaFree(ctx->d_comb_g2);
+  if (ctx->copy_stream) {
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamDestroy(ctx->copy_stream);
+  }
+  if (ctx->ev_alloc) cudaEventDestroy(ctx->ev_alloc);
+  if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -1093,7 +1104,7 @@ static int launch_coop_groups(bn254_ctx* ctx, int which, size_t n, size_t n_pad,
 
 // msgs == NULL: check_public_keys form (first G1 argument = generator, no hashing)
 static int verify_dev_impl(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, const uint8_t* sigs, const uint8_t* pks, size_t n,
-                           uint8_t* status) {
+                           uint8_t* status, cudaEvent_t inputs_ready = nullptr) {
   const bool coop = ctx->pairing_mode != 1;
   const bool wl = ctx->pairing_mode == 3 || (ctx->pairing_mode == 0 && ctx->coop_w);
   const bool hl = !wl && (ctx->pairing_mode == 4 || (ctx->pairing_mode == 0 && ctx->coop_h));
@@ -1128,6 +1139,7 @@ static int verify_dev_impl(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, 
       }
       h = H.as<g1aff>() + off;
     }
+    if (inputs_ready && off == 0) CK(cudaStreamWaitEvent(ctx->stream, inputs_ready, 0));  // sigs / pks arrive on the copy stream
     CK(mark());
     if (coop) {
       size_t m_pad = (m + COOP_LANES - 1) / COOP_LANES * COOP_LANES;
@@ -1201,11 +1213,19 @@ int bn254_verify_batch(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, cons
   DALLOC(d_sigs, 64 * n);
   DALLOC(d_pks, 128 * n);
   DALLOC(d_st, n);
+  // the messages go first on the compute stream (the hash needs nothing else); signatures and keys (6/7 of the bytes) are
+  // uploaded on the copy stream while the hash kernels run, and the line-set kernel waits for them
+  CK(cudaEventRecord(ctx->ev_alloc, ctx->stream));  // the buffers exist (stream-ordered allocation) from here on
+  CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_alloc, 0));
+  CK(cudaMemcpyAsync(d_sigs.p, sigs, 64 * n, cudaMemcpyHostToDevice, ctx->copy_stream));
+  CK(cudaMemcpyAsync(d_pks.p, pks, 128 * n, cudaMemcpyHostToDevice, ctx->copy_stream));
+  CK(cudaEventRecord(ctx->ev_copy, ctx->copy_stream));
   if (msg_len) H2D(d_msgs.p, msgs, msg_len * n);
-  H2D(d_sigs.p, sigs, 64 * n);
-  H2D(d_pks.p, pks, 128 * n);
-  int rc = verify_dev_impl(ctx, d_msgs.as<uint8_t>(), msg_len, d_sigs.as<uint8_t>(), d_pks.as<uint8_t>(), n, d_st.as<uint8_t>());
-  if (rc) return rc;
+  int rc = verify_dev_impl(ctx, d_msgs.as<uint8_t>(), msg_len, d_sigs.as<uint8_t>(), d_pks.as<uint8_t>(), n, d_st.as<uint8_t>(), ctx->ev_copy);
+  if (rc) {
+    cudaStreamSynchronize(ctx->copy_stream);
+    return rc;
+  }
   D2H(status, d_st.p, n);
   CK(cudaStreamSynchronize(ctx->stream));
   return 0;
