@@ -7,6 +7,8 @@
 //! On top of the reference API there are the batch entry points the engine exists for ([`ECDSA::verify_batch`],
 //! [`ECDSA::sign_batch`], [`ECDSA::verify_batch_randomized`], [`aggregate_verify_distinct`]).
 //!
+//! The raw declarations in `sys.rs` are generated from `include/bn254_b200.h` (`scripts/gen_rust_sys.py`) and a test of the
+//! engine's repository fails when the two drift apart.
 //! This crate is NOT built in the engine's own repository (its image has no Rust toolchain); the Python mirror
 //! `bn254_b200/api.py` is what the parity tests drive.  Differences from the reference, all forced by the byte-level
 //! representation: the inner field of the newtypes is a byte array instead of a `bn` struct, and the point at infinity
@@ -85,6 +87,10 @@ fn engine_call<F: FnOnce(*mut sys::bn254_ctx) -> c_int>(f: F) -> Result<()> {
         if rc != 0 {
             return Err(Error::Engine(last_error(std::ptr::null_mut())));
         }
+        // Every point this crate hands to the engine is a value of its own types: made by a validating constructor
+        // (from_compressed / from_uncompressed / from_private_key) or by + - on such values, so infinity is a legal value
+        // and G2 membership is an invariant -- exactly the engine's BN254_INPUTS_TYPED policy (include/bn254_b200.h).
+        unsafe { sys::bn254_set_input_policy(raw, sys::BN254_INPUTS_TYPED) };
         *guard = Some(Ctx(raw));
     }
     let ctx = guard.as_ref().unwrap().0;
@@ -106,41 +112,54 @@ fn last_error(ctx: *mut sys::bn254_ctx) -> String {
 }
 
 // ------------------------------------------------------------------------------------------------ PrivateKey
-/// `src/types.rs:13-77`.  Any 32 bytes are accepted and reduced mod r by the engine, as `Fr::from_slice` does.
-#[derive(Copy, Clone, Debug)]
-pub struct PrivateKey(pub [u8; 32]);
+/// `src/types.rs:13-77`.  Any 32 bytes are accepted and reduced mod r, as `Fr::from_slice` does; the field always holds
+/// the CANONICAL big-endian scalar, so equal keys compare equal (the reference derives `PartialEq` on the `Fr` inside).
+#[derive(Copy, Clone, Debug, PartialEq, Eq)]
+pub struct PrivateKey([u8; 32]);
+
+const R_ORDER: [u8; 32] = [
+    0x30, 0x64, 0x4e, 0x72, 0xe1, 0x31, 0xa0, 0x29, 0xb8, 0x50, 0x45, 0xb6, 0x81, 0x81, 0x58, 0x5d, 0x28, 0x33, 0xe8, 0x48, 0x79, 0xb9,
+    0x70, 0x91, 0x43, 0xe1, 0xf5, 0x93, 0xf0, 0x00, 0x00, 0x01,
+];
+/// any 256-bit big-endian integer mod r (2^256 / r < 6: at most five subtractions)
+fn reduce_mod_r(mut k: [u8; 32]) -> [u8; 32] {
+    while k >= R_ORDER {
+        let mut borrow = 0i16;
+        for i in (0..32).rev() {
+            let d = k[i] as i16 - R_ORDER[i] as i16 - borrow;
+            borrow = (d < 0) as i16;
+            k[i] = (d + 256 * borrow) as u8;
+        }
+    }
+    k
+}
 
 impl PrivateKey {
-    /// `src/types.rs:17-25`
+    /// `src/types.rs:17-25`: uniform in [0, r) like `Fr::random` (rejection sampling on 254-bit draws: 2^254 / r < 1.33)
     pub fn random<R: rand::Rng>(rng: &mut R) -> Self {
-        let mut b = [0u8; 32];
-        rng.fill_bytes(&mut b);
-        b[0] &= 0x1f; // below 2^253 < r: already canonical, so to_bytes returns what was drawn
-        PrivateKey(b)
-    }
-    /// `src/types.rs:27-29`: canonical big-endian scalar (the reduction is applied here, on the host: at most five subtractions)
-    pub fn to_bytes(&self) -> Result<Vec<u8>> {
-        const R: [u8; 32] = [
-            0x30, 0x64, 0x4e, 0x72, 0xe1, 0x31, 0xa0, 0x29, 0xb8, 0x50, 0x45, 0xb6, 0x81, 0x81, 0x58, 0x5d, 0x28, 0x33, 0xe8, 0x48, 0x79,
-            0xb9, 0x70, 0x91, 0x43, 0xe1, 0xf5, 0x93, 0xf0, 0x00, 0x00, 0x01,
-        ];
-        let mut k = self.0;
-        while k >= R {
-            let mut borrow = 0i16;
-            for i in (0..32).rev() {
-                let d = k[i] as i16 - R[i] as i16 - borrow;
-                borrow = (d < 0) as i16;
-                k[i] = (d + 256 * borrow) as u8;
+        loop {
+            let mut b = [0u8; 32];
+            rng.fill_bytes(&mut b);
+            b[0] &= 0x3f;
+            if b < R_ORDER {
+                return PrivateKey(b);
             }
         }
-        Ok(k.to_vec())
+    }
+    /// `src/types.rs:27-29`: canonical big-endian scalar
+    pub fn to_bytes(&self) -> Result<Vec<u8>> {
+        Ok(self.0.to_vec())
+    }
+    /// the canonical 32 bytes (what the engine is given)
+    pub fn as_bytes(&self) -> &[u8; 32] {
+        &self.0
     }
 }
 impl TryFrom<&[u8]> for PrivateKey {
     type Error = Error;
     fn try_from(b: &[u8]) -> Result<Self> {
         let a: [u8; 32] = b.try_into().map_err(|_| Error::InvalidLength)?; // src/types_test.rs:29-46
-        Ok(PrivateKey(a))
+        Ok(PrivateKey(reduce_mod_r(a)))
     }
 }
 impl TryFrom<&str> for PrivateKey {
@@ -164,16 +183,16 @@ impl TryFrom<PrivateKey> for String {
 
 // ------------------------------------------------------------------------------------------------ group elements
 macro_rules! point_type {
-    ($name:ident, $raw:expr, $comp:expr, $sum:path, $compress:path, $decompress:path, $validate:path, $doc:expr) => {
+    ($name:ident, $raw:expr, $comp:expr, $sum:path, $compress:path, $decompress:path, $validate:path, $doc:expr $(, $derive:ident)*) => {
         #[doc = $doc]
-        #[derive(Copy, Clone, Debug)]
+        #[derive(Copy, Clone, Debug $(, $derive)*)]
         pub struct $name(pub [u8; $raw]);
 
         impl $name {
             pub fn from_compressed<T: AsRef<[u8]>>(bytes: T) -> Result<Self> {
                 let b = bytes.as_ref();
                 if b.len() != $comp {
-                    return Err(Error::InvalidLength);
+                    return Err(Error::InvalidEncoding); // bn::G1 / G2::from_compressed: CurveError::InvalidEncoding
                 }
                 let (mut out, mut st) = ([0u8; $raw], 0u8);
                 engine_call(|c| unsafe { $decompress(c, b.as_ptr(), 1, out.as_mut_ptr(), &mut st) })?;
@@ -231,9 +250,10 @@ macro_rules! point_type {
     };
 }
 point_type!(PublicKey, 128, 65, sys::bn254_g2_sum, sys::bn254_g2_compress_batch, sys::bn254_g2_decompress_batch,
-            sys::bn254_g2_validate_batch, "`src/types.rs:81-148`: a G2 point, `x.re || x.im || y.re || y.im` big-endian.");
+            sys::bn254_g2_validate_batch, "`src/types.rs:81-148`: a G2 point, `x.re || x.im || y.re || y.im` big-endian.", PartialEq, Eq);
 point_type!(PublicKeyG1, 64, 33, sys::bn254_g1_sum, sys::bn254_g1_compress_batch, sys::bn254_g1_decompress_batch,
-            sys::bn254_g1_validate_batch, "`src/types.rs:151-218`: a G1 point, `x || y` big-endian.");
+            sys::bn254_g1_validate_batch, "`src/types.rs:151-218`: a G1 point, `x || y` big-endian.", PartialEq, Eq);
+// (the reference derives no PartialEq on Signature, src/types.rs:221)
 point_type!(Signature, 64, 33, sys::bn254_g1_sum, sys::bn254_g1_compress_batch, sys::bn254_g1_decompress_batch,
             sys::bn254_g1_validate_batch, "`src/types.rs:221-286`: a G1 point, `x || y` big-endian.");
 
@@ -241,7 +261,7 @@ impl PublicKey {
     /// `src/types.rs:85-87`: `G2::one() * sk`
     pub fn from_private_key(private_key: &PrivateKey) -> Self {
         let mut out = [0u8; 128];
-        engine_call(|c| unsafe { sys::bn254_derive_pk_g2_batch(c, private_key.0.as_ptr(), 1, out.as_mut_ptr()) }).expect("bn254_b200 engine");
+        engine_call(|c| unsafe { sys::bn254_derive_pk_g2_batch(c, private_key.as_bytes().as_ptr(), 1, out.as_mut_ptr()) }).expect("bn254_b200 engine");
         PublicKey(out)
     }
 }
@@ -249,7 +269,7 @@ impl PublicKeyG1 {
     /// `src/types.rs:155-157`: `G1::one() * sk`
     pub fn from_private_key(private_key: &PrivateKey) -> Self {
         let mut out = [0u8; 64];
-        engine_call(|c| unsafe { sys::bn254_derive_pk_g1_batch(c, private_key.0.as_ptr(), 1, out.as_mut_ptr()) }).expect("bn254_b200 engine");
+        engine_call(|c| unsafe { sys::bn254_derive_pk_g1_batch(c, private_key.as_bytes().as_ptr(), 1, out.as_mut_ptr()) }).expect("bn254_b200 engine");
         PublicKeyG1(out)
     }
 }
@@ -263,7 +283,7 @@ impl ECDSA {
     pub fn sign<T: AsRef<[u8]>>(message: T, private_key: &PrivateKey) -> Result<Signature> {
         let m = message.as_ref();
         let (mut sig, mut st) = ([0u8; 64], 0u8);
-        engine_call(|c| unsafe { sys::bn254_sign_batch(c, m.as_ptr(), m.len(), private_key.0.as_ptr(), 1, sig.as_mut_ptr(), &mut st) })?;
+        engine_call(|c| unsafe { sys::bn254_sign_batch(c, m.as_ptr(), m.len(), private_key.as_bytes().as_ptr(), 1, sig.as_mut_ptr(), &mut st) })?;
         status_to_result(st)?;
         Ok(Signature(sig))
     }
@@ -280,7 +300,7 @@ impl ECDSA {
         if msgs.len() != n * msg_len {
             return Err(Error::InvalidLength);
         }
-        let sks: Vec<u8> = keys.iter().flat_map(|k| k.0).collect();
+        let sks: Vec<u8> = keys.iter().flat_map(|k| *k.as_bytes()).collect();
         let (mut sigs, mut st) = (vec![0u8; 64 * n], vec![0u8; n]);
         engine_call(|c| unsafe { sys::bn254_sign_batch(c, msgs.as_ptr(), msg_len, sks.as_ptr(), n, sigs.as_mut_ptr(), st.as_mut_ptr()) })?;
         Ok((0..n).map(|i| status_to_result(st[i]).map(|_| Signature(sigs[64 * i..64 * i + 64].try_into().unwrap()))).collect())
@@ -347,6 +367,44 @@ pub fn aggregate_verify_distinct(msgs: &[u8], msg_len: usize, pks: &[PublicKey],
     status_to_result(st)
 }
 
+/// `[(H(m), pk), (sig, -G2)]` with little-endian coordinates, the value `format_pairing_check_*` return (`src/utils.rs:197-239`)
+pub type PairingCheckValues = [([u8; 64], [u8; 128]); 2];
+
+fn format_values(message: &[u8], sig: &[u8], pk: &[u8], compressed: bool) -> Result<PairingCheckValues> {
+    let (mut out, mut st) = ([0u8; 384], 0u8);
+    engine_call(|c| unsafe {
+        sys::bn254_format_pairing_check_batch(c, message.as_ptr(), message.len(), sig.as_ptr(), pk.as_ptr(), 1, compressed as c_int, out.as_mut_ptr(), &mut st)
+    })?;
+    status_to_result(st)?;
+    Ok([(out[0..64].try_into().unwrap(), out[64..192].try_into().unwrap()), (out[192..256].try_into().unwrap(), out[256..384].try_into().unwrap())])
+}
+/// `src/utils.rs:197-216`: 33-byte compressed signature, 65-byte compressed public key
+pub fn format_pairing_check_values(message: Vec<u8>, signature: Vec<u8>, public_key: Vec<u8>) -> Result<PairingCheckValues> {
+    if public_key.len() != 65 || signature.len() != 33 {
+        return Err(Error::InvalidEncoding); // from_compressed of either point
+    }
+    format_values(&message, &signature, &public_key, true)
+}
+/// `src/utils.rs:218-239`: 64 / 128-byte uncompressed inputs, re-ordered without validation like the reference; a wrong
+/// length is the reference's `Vec<u8> -> [u8; N]` failure, `SerializationError` (`src/error.rs:64-68`)
+pub fn format_pairing_check_uncompressed_values(message: Vec<u8>, signature: Vec<u8>, public_key: Vec<u8>) -> Result<PairingCheckValues> {
+    if signature.len() != 64 || public_key.len() != 128 {
+        return Err(Error::SerializationError);
+    }
+    format_values(&message, &signature, &public_key, false)
+}
+
+/// `hash_to_try_and_increment` (`src/hash.rs:29-63`) for n messages of `msg_len` bytes: the uncompressed G1 points
+pub fn hash_to_g1_batch(msgs: &[u8], msg_len: usize) -> Result<Vec<Result<[u8; 64]>>> {
+    if msg_len == 0 || msgs.len() % msg_len != 0 {
+        return Err(Error::InvalidLength);
+    }
+    let n = msgs.len() / msg_len;
+    let (mut out, mut st) = (vec![0u8; 64 * n], vec![0u8; n]);
+    engine_call(|c| unsafe { sys::bn254_hash_to_g1_batch(c, msgs.as_ptr(), msg_len, n, out.as_mut_ptr(), st.as_mut_ptr()) })?;
+    Ok((0..n).map(|i| status_to_result(st[i]).map(|_| out[64 * i..64 * i + 64].try_into().unwrap())).collect())
+}
+
 // ------------------------------------------------------------------------------------------------ serde (src/serde.rs:10-56)
 #[cfg(feature = "serde")]
 mod serde_impl {
@@ -364,7 +422,7 @@ mod serde_impl {
     impl<'de> Deserialize<'de> for PrivateKey {
         fn deserialize<D: Deserializer<'de>>(d: D) -> Result<Self, D::Error> {
             let b = <[u8; 32]>::deserialize(d)?; // src/serde.rs:29
-            Ok(PrivateKey(b))
+            PrivateKey::try_from(&b[..]).map_err(D::Error::custom)
         }
     }
     impl Serialize for PublicKey {

@@ -9,7 +9,7 @@ LIB_PATH = os.environ.get("BN254_B200_LIB") or os.path.join(HERE, "libbn254_b200
 # every symbol include/bn254_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "bn254_ctx_create", "bn254_ctx_destroy", "bn254_last_error", "bn254_sync", "bn254_stream", "bn254_sm_count", "bn254_launch_count",
-    "bn254_set_profiling", "bn254_phase_ms", "bn254_set_pairing_mode",
+    "bn254_set_profiling", "bn254_phase_ms", "bn254_set_pairing_mode", "bn254_trim", "bn254_set_input_policy", "bn254_get_input_policy", "bn254_set_hash_try_limit",
     "bn254_hash_to_g1_batch", "bn254_hash_to_g1_batch_dev", "bn254_hash_to_g1_var",
     "bn254_sign_batch", "bn254_sign_batch_dev", "bn254_verify_batch", "bn254_verify_batch_dev",
     "bn254_verify_batch_rlc", "bn254_verify_batch_rlc_dev",
@@ -18,7 +18,8 @@ SYMBOLS = [
     "bn254_derive_pk_g2_batch", "bn254_derive_pk_g1_batch", "bn254_g1_mul_batch", "bn254_g2_mul_batch",
     "bn254_g1_compress_batch", "bn254_g1_decompress_batch", "bn254_g2_compress_batch", "bn254_g2_decompress_batch",
     "bn254_g1_validate_batch", "bn254_g2_validate_batch",
-    "bn254_aggregate_verify_same_msg", "bn254_aggregate_verify_distinct",
+    "bn254_aggregate_verify_same_msg", "bn254_aggregate_verify_same_msg_dev", "bn254_aggregate_verify_distinct",
+    "bn254_distinct_payload_dev", "bn254_finish_distinct_dev", "bn254_format_pairing_check_batch",
     "bn254_miller_partial_distinct", "bn254_miller_partial_distinct_dev", "bn254_finish_distinct",
     "bn254_miller_loop_batch", "bn254_final_exp_batch", "bn254_fq_op_batch", "bn254_fq12_op_batch", "bn254_layer_op_batch",
 ]
@@ -46,6 +47,7 @@ def load():
         lib.bn254_ctx_destroy.argtypes = [ctypes.c_void_p]
         lib.bn254_ctx_destroy.restype = None
         lib.bn254_sync.argtypes = [ctypes.c_void_p]
+        lib.bn254_get_input_policy.argtypes = [ctypes.c_void_p]
         _lib = lib
     return _lib
 
@@ -112,6 +114,10 @@ class Context:
         rc = self.lib.bn254_sync(self.h)
         if rc != 0:
             raise EngineError("bn254_sync failed: %s" % self.lib.bn254_last_error(self.h).decode())
+
+    @property
+    def input_policy(self):
+        return int(self.lib.bn254_get_input_policy(self.h))
 
     @property
     def stream(self):

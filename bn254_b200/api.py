@@ -12,7 +12,8 @@ Every arithmetic operation runs on the GPU through the C ABI (batch size 1 here;
 bn254_b200.engine).  Points are held as the crate's uncompressed bytes (all-zero = the point at infinity, which
 the crate can hold but not serialise).
 """
-from . import engine as E
+from . import engine as _engine
+from ._native import Context
 
 ERROR_NAMES = {
     1: "HashToPointError", 2: "IndexOutOfBounds", 3: "InvalidEncoding", 4: "InvalidGroupPoint", 5: "InvalidLength",
@@ -28,6 +29,27 @@ class Error(Exception):
         self.code = int(code)
         self.variant = ERROR_NAMES.get(self.code, "Unknown(%d)" % self.code)
         super().__init__(self.variant)
+
+
+class _TypedEngine:
+    """The engine module bound to a context of its own with BN254_INPUTS_TYPED: the objects below ARE values of the crate's
+    types (validated by their constructors, possibly infinity after + / -), which is exactly what that policy means."""
+
+    def __init__(self):
+        self._ctx = None
+
+    def ctx(self):
+        if self._ctx is None:
+            self._ctx = Context(0)
+            _engine.set_input_policy(_engine.INPUTS_TYPED, ctx=self._ctx)
+        return self._ctx
+
+    def __getattr__(self, name):
+        fn = getattr(_engine, name)
+        return lambda *a, **k: fn(*a, ctx=self.ctx(), **k)
+
+
+E = _TypedEngine()
 
 
 def _check(st):
@@ -215,28 +237,28 @@ NEG_G2_UNCOMPRESSED = bytes.fromhex(
     "275dc4a288d1afb3cbb1ac09187524c7db36395df7be3b99e673b13a075a65ec")
 
 
-def _le_chunks(b):
-    return b"".join(b[i:i + 32][::-1] for i in range(0, len(b), 32))
-
-
-def _pairing_check_values(message, sig_raw, pk_raw):
-    message = bytes(message)
-    h, st = E.hash_to_g1_batch(message if message else None, len(message), 1)
-    _check(st[0])
-    return [(_le_chunks(h), _le_chunks(pk_raw)), (_le_chunks(sig_raw), _le_chunks(NEG_G2_UNCOMPRESSED))]
+def _pairs(blob):
+    return [(blob[0:64], blob[64:192]), (blob[192:256], blob[256:384])]
 
 
 def format_pairing_check_values(message, signature, public_key):
     """(message, 33-byte compressed signature, 65-byte compressed public key) -> [(H(m), pk), (sig, -G2)]"""
-    pk = PublicKey.from_compressed(public_key)
-    sig = Signature.from_compressed(signature)
-    return _pairing_check_values(message, sig.to_uncompressed(), pk.to_uncompressed())
+    message, signature, public_key = bytes(message), bytes(signature), bytes(public_key)
+    if len(public_key) != 65 or len(signature) != 33:
+        raise Error(3)  # InvalidEncoding from bn::G2 / G1::from_compressed (public key first, like the reference)
+    blob, st = E.format_pairing_check_batch(message if message else None, len(message), signature, public_key, True)
+    _check(st[0])
+    return _pairs(blob)
 
 
 def format_pairing_check_uncompressed_values(message, signature, public_key):
     """(message, 64-byte uncompressed signature, 128-byte uncompressed public key); like the reference, the point bytes
     are re-ordered without being validated (/root/reference/src/utils.rs:218-239)."""
-    signature, public_key = bytes(signature), bytes(public_key)
+    message, signature, public_key = bytes(message), bytes(signature), bytes(public_key)
     if len(signature) != 64 or len(public_key) != 128:
-        raise Error(5)  # the reference's try_into fails with the Vec<u8> -> InvalidLength mapping (src/error.rs:64-68)
-    return _pairing_check_values(message, signature, public_key)
+        # over-long inputs: the reference's Vec<u8> -> [u8; N] try_into fails, which maps to SerializationError
+        # (/root/reference/src/error.rs:64-68); shorter ones make its slice indexing panic -- reported the same way here
+        raise Error(10)
+    blob, st = E.format_pairing_check_batch(message if message else None, len(message), signature, public_key, False)
+    _check(st[0])
+    return _pairs(blob)

@@ -49,14 +49,14 @@ __global__ void k_init_lines(line_t* out) {
 // hash_to_try_and_increment for message i = msgs[i*msg_len ..] (offsets == NULL) or msgs[offsets[i] .. offsets[i+1])
 __global__ void __launch_bounds__(BN_BLOCK) k_hash_to_g1(const uint8_t* __restrict__ msgs, size_t msg_len, const uint64_t* __restrict__ offsets,
                                                          size_t n, g1aff* __restrict__ H, uint8_t* __restrict__ status,
-                                                         uint8_t* __restrict__ tries) {
+                                                         uint8_t* __restrict__ tries, int max_tries) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint8_t* m = offsets ? msgs + offsets[i] : msgs + i * msg_len;
   uint64_t len = offsets ? offsets[i + 1] - offsets[i] : msg_len;
   g1aff h;
   int ctr = 0;
-  int st = hash_to_g1(&h.x, &h.y, m, len, &ctr);
+  int st = hash_to_g1(&h.x, &h.y, m, len, &ctr, max_tries);
   if (st) {
     h.x = fq_zero();
     h.y = fq_zero();
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(BN_BLOCK) k_hash_round(const uint8_t* __restri
   }
 }
 // the few items that survive the compacting rounds finish with the per-thread loop (counters ctr0 .. 254)
-__global__ void __launch_bounds__(BN_BLOCK) k_hash_tail(const uint8_t* __restrict__ msgs, uint32_t msg_len, uint32_t ctr0,
+__global__ void __launch_bounds__(BN_BLOCK) k_hash_tail(const uint8_t* __restrict__ msgs, uint32_t msg_len, uint32_t ctr0, uint32_t max_tries,
                                                         const uint32_t* __restrict__ list_in, const uint32_t* __restrict__ count_in,
                                                         g1aff* __restrict__ H, uint8_t* __restrict__ status) {
   const uint32_t total = *count_in;
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(BN_BLOCK) k_hash_tail(const uint8_t* __restric
     const uint32_t i = list_in[t];
     g1aff h;
     bool ok = false;
-    for (uint32_t ctr = ctr0; ctr < 255 && !ok; ctr++) ok = hash_try_1blk(&h.x, &h.y, msgs + (size_t)i * msg_len, msg_len, ctr);
+    for (uint32_t ctr = ctr0; ctr < max_tries && !ok; ctr++) ok = hash_try_1blk(&h.x, &h.y, msgs + (size_t)i * msg_len, msg_len, ctr);
     if (!ok) {
       h.x = fq_zero();
       h.y = fq_zero();
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(BN_BLOCK, BN_MINB) k_verify_miller(const g1aff
                                                             uint8_t* __restrict__ status, const line_t* __restrict__ lines) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  if (H && status[i]) return;  // hash error propagates (/root/reference/src/ecdsa.rs:53)
+  if (status[i]) return;  // hash error propagates (/root/reference/src/ecdsa.rs:53); so does a validation error
   g1aff h;
   if (H) {
     h = H[i];
@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(BN_BLOCK, BN_LINES_MINB) k_verify_lines(const 
                                                            uint8_t* __restrict__ status, const line_t* __restrict__ table) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  if (H && status[i]) return;  // hash error propagates; the item's line sets stay unwritten and its verdict is never stored
+  if (status[i]) return;  // a hash or validation error propagates; the item's line sets stay unwritten and its verdict is never stored
   g1aff h;
   if (H) {
     h = H[i];
@@ -313,6 +313,19 @@ __global__ void __launch_bounds__(BN_BLOCK, BN_LINES_MINB) k_verify_lines(const 
   }
   __shared__ lines_consts consts[BN_BLOCK];
   status[i] = (uint8_t)item_verify_lines(lines, n_pad, i, &h, sigs + 64 * i, pks + 128 * i, table, &consts[threadIdx.x]);
+}
+
+// Untrusted-input policy (the default, bn254_set_input_policy): sig / pk bytes are decoded exactly as
+// Signature::from_uncompressed / PublicKey::from_uncompressed would decode them (/root/reference/src/utils.rs:107-127):
+// field membership, curve equation -- which (0, 0), the engine's encoding of infinity, fails -- and for G2 the r-torsion
+// test of AffineG2::new.  pk is decoded first, then sig; a decode error replaces whatever the hash left in status.
+__global__ void __launch_bounds__(BN_BLOCK) k_validate_inputs(const uint8_t* __restrict__ sigs, const uint8_t* __restrict__ pks, size_t n,
+                                                              uint8_t* __restrict__ status) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int st = item_g2_validate(pks + 128 * i);
+  if (!st) st = item_g1_validate(sigs + 64 * i);
+  if (st) status[i] = (uint8_t)st;
 }
 
 #if defined(COOP_ABLATE_NOBAR)  // timing experiment only: results are wrong without the barriers
@@ -327,7 +340,7 @@ __global__ void __launch_bounds__(BN_BLOCK, BN_LINES_MINB) k_verify_lines(const 
 #define BN_COOP_STAGGER 0
 #endif
 #ifndef BN_COOP_CHUNK_LOG2
-#define BN_COOP_CHUNK_LOG2 20
+#define BN_COOP_CHUNK_LOG2 19
 #endif
 #ifndef BN_COOP_DEFAULT_GROUPS4
 #define BN_COOP_DEFAULT_GROUPS4 1
@@ -368,7 +381,7 @@ __global__ void __launch_bounds__(COOP_THREADS, BN_COOP_MINB) k_coop_run(int whi
   c.gslots = gslots;
   c.fio = fio;
   c.status = status;
-  const uint32_t* prog = which == 0 ? K_COOP_PROG_VERIFY : which == 1 ? K_COOP_PROG_MILLER1 : which == 2 ? K_COOP_PROG_MILLER2 : which == 3 ? K_COOP_PROG_FINALEXP : K_COOP_PROG_MULTI;
+  const uint32_t* prog = coop_program(which);
   int line_next = 0;
 #pragma unroll 1
   for (int pc = 0;; pc++) {
@@ -414,7 +427,7 @@ __global__ void __launch_bounds__(COOP4_THREADS, 1) k_coop4_run(int which, size_
   c.gslots = gslots;
   c.fio = fio;
   c.status = status;
-  const uint32_t* prog = which == 0 ? K_COOP_PROG_VERIFY : which == 1 ? K_COOP_PROG_MILLER1 : which == 2 ? K_COOP_PROG_MILLER2 : which == 3 ? K_COOP_PROG_FINALEXP : K_COOP_PROG_MULTI;
+  const uint32_t* prog = coop_program(which);
   int line_next = 0;
   const int bar = g + 1;
 #pragma unroll 1
@@ -465,7 +478,7 @@ __global__ void __launch_bounds__(COOP4_THREADS, 1) k_cooph_run(int which, size_
   c.gslots = gslots;
   c.fio = fio;
   c.status = status;
-  const uint32_t* prog = which == 0 ? K_COOP_PROG_VERIFY : which == 1 ? K_COOP_PROG_MILLER1 : which == 2 ? K_COOP_PROG_MILLER2 : K_COOP_PROG_FINALEXP;
+  const uint32_t* prog = coop_program(which);
   // the second group of every sub-partition starts late, so that the two do not run their phases in step
   if (offset_cycles && g >= 4) {
     const long long t0 = clock64();
@@ -519,7 +532,7 @@ __global__ void __launch_bounds__(COOPW_WARPS * 32, BN_COOP_MINB) k_coopw_run(in
   c.gslots = gslots;
   c.fio = fio;
   c.status = status;
-  const uint32_t* prog = which == 0 ? K_COOP_PROG_VERIFY : which == 1 ? K_COOP_PROG_MILLER1 : which == 2 ? K_COOP_PROG_MILLER2 : K_COOP_PROG_FINALEXP;
+  const uint32_t* prog = coop_program(which);
   int line_next = 0;
 #pragma unroll 1
   for (int pc = 0;; pc++) {
@@ -542,23 +555,40 @@ __global__ void __launch_bounds__(COOPW_WARPS * 32, BN_COOP_MINB) k_coopw_run(in
 
 // ---- multi-pairing through the cooperative machine: pair p is stream p / L of lane p % L (L lanes, COOP_MULTI_K streams each)
 __device__ __forceinline__ void record_error(unsigned long long* err, size_t i, int st);
+// mk = pairs per lane of the consuming program.  extra_sig != NULL: pair number n is (that G1 point, -G2) -- the rank's own
+// share of the second pairing of the aggregate check, folded into its Miller product (bilinearity: the product over the
+// ranks of e(S_r, -G2) is e(sum S_r, -G2)); an all-zero extra_sig (infinity) is skipped like any pair holding an infinity.
 __global__ void __launch_bounds__(BN_BLOCK, BN_LINES_MINB) k_pair_lines(const g1aff* __restrict__ H, const uint8_t* __restrict__ hstatus,
-                                                                        const uint8_t* __restrict__ pks, size_t n, size_t L,
+                                                                        const uint8_t* __restrict__ pks, size_t n, size_t L, int mk,
                                                                         u4* __restrict__ lines, unsigned long long* __restrict__ err,
-                                                                        size_t index_base) {
+                                                                        size_t index_base, const uint8_t* __restrict__ extra_sig,
+                                                                        int typed) {
   __shared__ lines_consts consts[BN_BLOCK];
   size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= L * COOP_MULTI_K) return;
+  if (p >= L * (size_t)mk) return;
   bool use = false;
   g1aff h;
   g2j q;
   q.x = fq2_one();
   q.y = fq2_one();
-  if (p < n) {
+  if (extra_sig && p == n) {
+    g1j s;
+    int st = g1_from_raw(&s, extra_sig);
+    if (st) record_error(err, index_base + p, st);
+    else if (!pt_is_inf(&s)) {
+      use = true;
+      h.x = s.x;
+      h.y = s.y;
+      q.x = fq2_from_limbs(K_G2_GEN_X);
+      q.y = fq2_neg(fq2_from_limbs(K_G2_GEN_Y));
+    }
+  } else if (p < n) {
     if (hstatus[p]) {
       record_error(err, index_base + p, hstatus[p]);
     } else {
-      int st = g2_from_raw(&q, pks + 128 * p);
+      // untrusted keys are decoded like PublicKey::from_uncompressed (r-torsion test included, no infinity)
+      int st = typed ? g2_from_raw(&q, pks + 128 * p) : item_g2_validate(pks + 128 * p);
+      if (!st && !typed) st = g2_from_raw(&q, pks + 128 * p);
       if (st) record_error(err, index_base + p, st);
       else if (!pt_is_inf(&q)) {
         use = true;
@@ -566,7 +596,7 @@ __global__ void __launch_bounds__(BN_BLOCK, BN_LINES_MINB) k_pair_lines(const g1
       }
     }
   }
-  item_pair_lines(lines, L, p % L, (int)(p / L), use, &h, q.x, q.y, &consts[threadIdx.x]);
+  item_pair_lines(lines, L, p % L, (int)(p / L), mk, use, &h, q.x, q.y, &consts[threadIdx.x]);
 }
 // lane 0 of every block holds the block's product (power-basis layout fio) -> tower-order Fq12 array
 __global__ void k_coop_gather(const u4* __restrict__ fio, size_t L, size_t blocks, fq12* __restrict__ out) {
@@ -659,11 +689,13 @@ template <class F> struct pt_io;
 template <> struct pt_io<fq> {
   static const int BYTES = 64;
   static __device__ int load(jac<fq>* p, const uint8_t* b) { return g1_from_raw(p, b); }
+  static __device__ int validate(const uint8_t* b) { return item_g1_validate(b); }
   static __device__ void store(uint8_t* b, const jac<fq>* p) { g1_to_raw(b, p); }
 };
 template <> struct pt_io<fq2> {
   static const int BYTES = 128;
   static __device__ int load(jac<fq2>* p, const uint8_t* b) { return g2_from_raw(p, b); }
+  static __device__ int validate(const uint8_t* b) { return item_g2_validate(b); }
   static __device__ void store(uint8_t* b, const jac<fq2>* p) { g2_to_raw(b, p); }
 };
 __device__ __forceinline__ void record_error(unsigned long long* err, size_t i, int st) {
@@ -672,7 +704,7 @@ __device__ __forceinline__ void record_error(unsigned long long* err, size_t i, 
 
 template <class F>
 __global__ void __launch_bounds__(BN_BLOCK) k_sum_partial(const uint8_t* __restrict__ pts, const uint8_t* __restrict__ neg, size_t n,
-                                                          jac<F>* __restrict__ partial, unsigned long long* __restrict__ err) {
+                                                          jac<F>* __restrict__ partial, unsigned long long* __restrict__ err, int strict) {
   __shared__ jac<F> sh[BN_BLOCK];
   const int B = pt_io<F>::BYTES;
   jac<F> acc;
@@ -680,7 +712,9 @@ __global__ void __launch_bounds__(BN_BLOCK) k_sum_partial(const uint8_t* __restr
   size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     jac<F> p;
-    int st = pt_io<F>::load(&p, pts + (size_t)B * i);
+    // strict: bytes from outside are decoded like from_uncompressed (no infinity, G2 in the r-torsion)
+    int st = strict ? pt_io<F>::validate(pts + (size_t)B * i) : ST_OK;
+    if (!st) st = pt_io<F>::load(&p, pts + (size_t)B * i);
     if (st) {
       record_error(err, i, st);
       continue;
@@ -725,7 +759,7 @@ __global__ void __launch_bounds__(BN_BLOCK) k_sum_final(const jac<F>* __restrict
 // ---- distinct-message multi-pairing: every thread folds the Miller values of its strided pairs into one Fq12
 __global__ void __launch_bounds__(BN_PROD_BLOCK) k_distinct_partial(const g1aff* __restrict__ H, const uint8_t* __restrict__ hstatus,
                                                                      const uint8_t* __restrict__ pks, size_t n, fq12* __restrict__ partial,
-                                                                     unsigned long long* __restrict__ err) {
+                                                                     unsigned long long* __restrict__ err, int typed) {
   __shared__ fq12 sh[BN_PROD_BLOCK];
   fq12 acc;
   fq12_set_one(&acc);
@@ -736,7 +770,8 @@ __global__ void __launch_bounds__(BN_PROD_BLOCK) k_distinct_partial(const g1aff*
       continue;
     }
     g2j q;
-    int st = g2_from_raw(&q, pks + 128 * i);
+    int st = typed ? ST_OK : item_g2_validate(pks + 128 * i);
+    if (!st) st = g2_from_raw(&q, pks + 128 * i);
     if (st) {
       record_error(err, i, st);
       continue;
@@ -754,6 +789,21 @@ __global__ void __launch_bounds__(BN_PROD_BLOCK) k_distinct_partial(const g1aff*
     __syncthreads();
   }
   if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+// one-thread-per-item mode: the Miller value of the extra pair (sig, -G2) of a rank's partial
+__global__ void k_extra_pair(const uint8_t* __restrict__ sig, const line_t* __restrict__ lines, fq12* __restrict__ out,
+                             unsigned long long* __restrict__ err, size_t index) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  fq12 t;
+  fq12_set_one(&t);
+  g1j s;
+  int st = g1_from_raw(&s, sig);
+  if (st) record_error(err, index, st);
+  else if (!pt_is_inf(&s)) {
+    fq2 dummy = fq2_one();
+    miller_loop_2(&t, false, &s.x, &s.y, &dummy, &dummy, true, &s.x, &s.y, lines);
+  }
+  *out = t;
 }
 // product of m Fq12 partials -> one Fq12 (Montgomery form) and its 384-byte big-endian image
 __global__ void __launch_bounds__(BN_PROD_BLOCK) k_fq12_prod_final(const fq12* __restrict__ partial, int m, fq12* __restrict__ out,
@@ -781,21 +831,103 @@ __global__ void __launch_bounds__(BN_PROD_BLOCK) k_fq12_prod_final(const fq12* _
     }
   }
 }
+// one level of the product tree: block b folds partial[b * per .. (b + 1) * per) into out[b]
+__global__ void __launch_bounds__(BN_PROD_BLOCK) k_fq12_prod_level(const fq12* __restrict__ partial, size_t m, size_t per, fq12* __restrict__ out) {
+  __shared__ fq12 sh[BN_PROD_BLOCK];
+  fq12 acc;
+  fq12_set_one(&acc);
+  const size_t lo = (size_t)blockIdx.x * per, hi = lo + per < m ? lo + per : m;
+  for (size_t i = lo + threadIdx.x; i < hi; i += BN_PROD_BLOCK) {
+    fq12 t = partial[i];
+    fq12_mul(&acc, &acc, &t);
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = BN_PROD_BLOCK / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) fq12_mul(&sh[threadIdx.x], &sh[threadIdx.x], &sh[threadIdx.x + s]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = sh[0];
+}
+
+// ---- finish of an aggregate check through the cooperative machine (one item): the exchanged payloads are folded here
+// payload r (BN254_DISTINCT_PAYLOAD bytes): [0, 384) Miller partial (big-endian, tower order), [384] its status, [385] 1 when
+// the rank's own (sum of signatures, -G2) pair is already inside its partial.  Thread t folds payload t, t + 64, ...; the
+// product goes to fio in the machine's layout (item 0 of a 32-item group), the 87 scaled -G2 lines of agg_sig (or the
+// constant 1 when agg_sig is NULL / infinity) to `lines`, and *status gets the first payload error in rank order (the
+// machine's CHECK never overwrites an error).
+#define BN_PAYLOAD 448
+__global__ void __launch_bounds__(BN_BLOCK) k_finish_prepare(const uint8_t* __restrict__ payloads, int m, const uint8_t* __restrict__ agg_sig,
+                                                             const line_t* __restrict__ table, u4* __restrict__ lines, u4* __restrict__ fio,
+                                                             uint8_t* __restrict__ status) {
+  __shared__ fq12 sh[BN_PROD_BLOCK];
+  __shared__ int first_err;
+  __shared__ lines_consts sconst;
+  if (threadIdx.x == 0) first_err = 0x7fffffff;
+  __syncthreads();
+  if (threadIdx.x < BN_PROD_BLOCK) {
+    fq12 acc, t;
+    fq12_set_one(&acc);
+    for (int i = threadIdx.x; i < m; i += BN_PROD_BLOCK) {
+      const uint8_t* pl = payloads + (size_t)BN_PAYLOAD * i;
+      int st = pl[384];
+      if (!st && !fq12_from_be(&t, pl)) st = ST_NOT_MEMBER;
+      if (st) atomicMin(&first_err, (i << 8) | st);
+      else fq12_mul(&acc, &acc, &t);
+    }
+    sh[threadIdx.x] = acc;
+  }
+  __syncthreads();
+  for (int s = BN_PROD_BLOCK / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) fq12_mul(&sh[threadIdx.x], &sh[threadIdx.x], &sh[threadIdx.x + s]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    g1j sg;
+    pt_set_inf(&sg);
+    int st = agg_sig ? g1_from_raw(&sg, agg_sig) : ST_OK;
+    if (st) atomicMin(&first_err, (m << 8) | st);
+    sconst.v[3].c0 = sg.x;
+    sconst.v[3].c1 = sg.y;
+    sconst.v[2].c0 = pt_is_inf(&sg) ? fq_zero() : fq_one();  // "use" flag for the line writers
+    const int pos[6] = {0, 2, 4, 1, 3, 5};  // tower order (c0.c0, c0.c1, c0.c2, c1.c0, c1.c1, c1.c2) -> power-basis coefficient
+    const fq2* c = &sh[0].c0.c0;
+    for (int t = 0; t < 6; t++) {
+      coop_gst(fio, (size_t)pos[t] * 2 + 0, COOP_LANES, 0, c[t].c0);
+      coop_gst(fio, (size_t)pos[t] * 2 + 1, COOP_LANES, 0, c[t].c1);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < K_N_LINES) {
+    const int mline = threadIdx.x;
+    const bool use = !fq_is_zero(sconst.v[2].c0);
+    coop_emit_scaled_v(lines, mline, COOP_LANES, 0, use, table[mline].ell_0, table[mline].ell_vw, table[mline].ell_vv, sconst.v[3]);
+  }
+  if (threadIdx.x == 0) *status = first_err == 0x7fffffff ? 0 : (uint8_t)(first_err & 0xff);
+}
+
 // prod(partials) * miller(agg_sig, -G2), final exponentiation, verdict
-__global__ void k_distinct_finish(const uint8_t* __restrict__ partials_be, int m, const uint8_t* __restrict__ agg_sig,
+// (the one-thread form: pairing mode 1, and the cross-check of the cooperative finish in the tests)
+__global__ void k_distinct_finish(const uint8_t* __restrict__ payloads, int m, const uint8_t* __restrict__ agg_sig,
                                   const line_t* __restrict__ lines, uint8_t* __restrict__ status) {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
   fq12 acc, t;
   fq12_set_one(&acc);
   for (int i = 0; i < m; i++) {
-    if (!fq12_from_be(&t, partials_be + 384 * i)) {
+    const uint8_t* pl = payloads + (size_t)BN_PAYLOAD * i;
+    if (pl[384]) {
+      *status = pl[384];
+      return;
+    }
+    if (!fq12_from_be(&t, pl)) {
       *status = ST_NOT_MEMBER;
       return;
     }
     fq12_mul(&acc, &acc, &t);
   }
   g1j s;
-  int st = g1_from_raw(&s, agg_sig);
+  pt_set_inf(&s);
+  int st = agg_sig ? g1_from_raw(&s, agg_sig) : ST_OK;
   if (st) {
     *status = (uint8_t)st;
     return;
@@ -806,6 +938,58 @@ __global__ void k_distinct_finish(const uint8_t* __restrict__ partials_be, int m
     fq12_mul(&acc, &acc, &t);
   }
   *status = item_final_exp_is_one(&acc);
+}
+
+// out = first non-zero of st[0 .. m)
+__global__ void k_first_status(const uint8_t* __restrict__ st, int m, uint8_t* __restrict__ out) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  uint8_t r = 0;
+  for (int i = 0; i < m && !r; i++) r = st[i];
+  *out = r;
+}
+// 32 big-endian bytes -> 32 little-endian bytes
+__device__ __forceinline__ void rev32(uint8_t* dst, const uint8_t* src) {
+  for (int i = 0; i < 32; i++) dst[i] = src[31 - i];
+}
+// /root/reference/src/utils.rs:197-239; the order of the error checks is the reference's: hash, public key, signature
+__global__ void __launch_bounds__(BN_BLOCK) k_format_pairing_check(const g1aff* __restrict__ H, const uint8_t* __restrict__ sigs,
+                                                                   const uint8_t* __restrict__ pks, size_t n, int compressed,
+                                                                   uint8_t* __restrict__ out, uint8_t* __restrict__ status) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint8_t* o = out + 384 * i;
+  int st = status[i];  // hash status
+  uint8_t sig[64], pk[128];
+  if (!st) {
+    if (compressed) {
+      st = item_g2_decompress(pk, pks + 65 * i);
+      if (!st) st = item_g1_decompress(sig, sigs + 33 * i);
+    } else {
+      for (int k = 0; k < 128; k++) pk[k] = pks[128 * i + k];
+      for (int k = 0; k < 64; k++) sig[k] = sigs[64 * i + k];
+    }
+  }
+  status[i] = (uint8_t)st;
+  if (st) {
+    for (int k = 0; k < 384; k++) o[k] = 0;
+    return;
+  }
+  uint8_t hb[64];
+  fq_to_be(hb, H[i].x);
+  fq_to_be(hb + 32, H[i].y);
+  rev32(o, hb);
+  rev32(o + 32, hb + 32);
+  for (int k = 0; k < 4; k++) rev32(o + 64 + 32 * k, pk + 32 * k);
+  rev32(o + 192, sig);
+  rev32(o + 224, sig + 32);
+  // -G2::one(): x.re, x.im, y.re, y.im of the negated generator
+  fq2 gx = fq2_from_limbs(K_G2_GEN_X), gy = fq2_neg(fq2_from_limbs(K_G2_GEN_Y));
+  uint8_t gb[128];
+  fq_to_be(gb, gx.c0);
+  fq_to_be(gb + 32, gx.c1);
+  fq_to_be(gb + 64, gy.c0);
+  fq_to_be(gb + 96, gy.c1);
+  for (int k = 0; k < 4; k++) rev32(o + 256 + 32 * k, gb + 32 * k);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -828,6 +1012,9 @@ struct bn254_ctx {
   int coop_groups4 = BN_COOP_DEFAULT_GROUPS4;  // block layout: four groups per 24-warp block, one group per sub-partition (k_coop4_run)
   bool coop_h = BN_COOP_DEFAULT_H;  // verify uses the half-warp layout (k_cooph_run, pairing mode 4)
   bool coop_w = BN_COOP_DEFAULT_W;  // layout mode 0 uses for verify (BN254_COOP_W=0/1 in the environment overrides)
+  cudaMemPool_t pool = nullptr;  // private stream-ordered pool: every temporary of this context comes from it and goes back on destroy
+  int input_policy = BN254_INPUTS_UNTRUSTED;
+  int hash_try_limit = 255;      // /root/reference/src/hash.rs:39; lowered only by the test hook bn254_set_hash_try_limit
   std::string err;
   // optional per-phase timing of the verify pipeline (bn254_set_profiling): events recorded on `stream`
   bool prof = false;
@@ -853,7 +1040,11 @@ struct dbuf {
   bn254_ctx* ctx;
   void* p = nullptr;
   dbuf(bn254_ctx* c) : ctx(c) {}
-  cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 1, ctx->stream); }
+  cudaError_t alloc(size_t bytes) { return cudaMallocFromPoolAsync(&p, bytes ? bytes : 1, ctx->pool, ctx->stream); }
+  void release() {
+    if (p) cudaFreeAsync(p, ctx->stream);
+    p = nullptr;
+  }
   ~dbuf() {
     if (p) cudaFreeAsync(p, ctx->stream);
   }
@@ -894,15 +1085,26 @@ int bn254_ctx_create(int device, bn254_ctx** out) {
   cudaDeviceProp prop;
   if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail("cudaGetDeviceProperties", e);
   ctx->sm_count = prop.multiProcessorCount;
-  if ((e = cudaDeviceSetLimit(cudaLimitStackSize, 16 * 1024)) != cudaSuccess) return fail("cudaDeviceSetLimit(stack)", e);
+  // the one-thread-per-item pairing kernels keep Fq12 temporaries on the stack; the limit is device-wide, so it is only ever raised
+  size_t stack_now = 0;
+  if (cudaDeviceGetLimit(&stack_now, cudaLimitStackSize) != cudaSuccess || stack_now < 16 * 1024)
+    if ((e = cudaDeviceSetLimit(cudaLimitStackSize, 16 * 1024)) != cudaSuccess) return fail("cudaDeviceSetLimit(stack)", e);
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
   if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate(copy)", e);
   if ((e = cudaEventCreateWithFlags(&ctx->ev_alloc, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
   if ((e = cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
-  cudaMemPool_t pool;
-  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+  // A private pool (the device's default pool is shared with the host process, e.g. torch): freed blocks stay cached here
+  // between calls -- the line-set workspace of verify is allocated once, not per call -- and everything is returned to the
+  // driver by bn254_ctx_destroy / bn254_trim.
+  {
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    if ((e = cudaMemPoolCreate(&ctx->pool, &props)) != cudaSuccess) return fail("cudaMemPoolCreate", e);
     uint64_t thr = UINT64_MAX;
-    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &thr);
   }
   if ((e = cudaMalloc(&ctx->d_lines, sizeof(line_t) * K_N_LINES)) != cudaSuccess) return fail("cudaMalloc(lines)", e);
   k_init_lines<<<1, 1, 0, ctx->stream>>>(ctx->d_lines);
@@ -940,6 +1142,7 @@ void bn254_ctx_destroy(bn254_ctx* ctx) {
   if (ctx->ev_alloc) cudaEventDestroy(ctx->ev_alloc);
   if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
   delete ctx;
 }
 const char* bn254_last_error(bn254_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
@@ -947,6 +1150,24 @@ int bn254_sync(bn254_ctx* ctx) {
   if (!ctx) return BN254_E_ARG;
   CK(cudaSetDevice(ctx->device));
   CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int bn254_trim(bn254_ctx* ctx) {
+  if (!ctx) return BN254_E_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemPoolTrimTo(ctx->pool, 0));
+  return 0;
+}
+int bn254_set_input_policy(bn254_ctx* ctx, int policy) {
+  if (!ctx || (policy != BN254_INPUTS_UNTRUSTED && policy != BN254_INPUTS_TYPED)) return BN254_E_ARG;
+  ctx->input_policy = policy;
+  return 0;
+}
+int bn254_get_input_policy(bn254_ctx* ctx) { return ctx ? ctx->input_policy : BN254_E_ARG; }
+int bn254_set_hash_try_limit(bn254_ctx* ctx, int max_tries) {
+  if (!ctx || max_tries < 1 || max_tries > 255) return BN254_E_ARG;
+  ctx->hash_try_limit = max_tries;
   return 0;
 }
 void* bn254_stream(bn254_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
@@ -983,8 +1204,9 @@ static int hash_dev(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, const u
                     uint8_t* tries) {
   if (n == 0) return 0;
   // small batches, ragged messages, multi-block messages and callers that want the counters: one thread loops per item
+  const int cap = ctx->hash_try_limit;
   if (offsets || tries || msg_len > 54 || n < 4096 || n > 0xffffffffu) {
-    LAUNCH(k_hash_to_g1, grid_for(n), BN_BLOCK, msgs, msg_len, offsets, n, H, status, tries);
+    LAUNCH(k_hash_to_g1, grid_for(n), BN_BLOCK, msgs, msg_len, offsets, n, H, status, tries, cap);
     return 0;
   }
   // compacting rounds: expected survivors of round r = n * 0.527^r; grids are sized with a margin and stride over the list
@@ -994,7 +1216,8 @@ static int hash_dev(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, const u
   uint32_t* L[2] = {lists.as<uint32_t>(), lists.as<uint32_t>() + n};
   uint32_t* C = counts.as<uint32_t>();
   double expect = (double)n;
-  for (int r = 0; r < BN_HASH_ROUNDS; r++) {
+  const int rounds = cap < BN_HASH_ROUNDS ? cap : BN_HASH_ROUNDS;  // (the tail below marks whatever is left after `cap` tries)
+  for (int r = 0; r < rounds; r++) {
     size_t threads = r == 0 ? n : (size_t)(expect * 1.25) + 4096;
     if (threads > n) threads = n;
     LAUNCH(k_hash_round, grid_for(threads), BN_BLOCK, msgs, (uint32_t)msg_len, (uint32_t)n, (uint32_t)r, r == 0 ? (const uint32_t*)nullptr : L[(r - 1) & 1],
@@ -1003,8 +1226,7 @@ static int hash_dev(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, const u
   }
   size_t threads = (size_t)(expect * 1.25) + 4096;
   if (threads > n) threads = n;
-  LAUNCH(k_hash_tail, grid_for(threads), BN_BLOCK, msgs, (uint32_t)msg_len, (uint32_t)BN_HASH_ROUNDS, L[(BN_HASH_ROUNDS - 1) & 1], C + BN_HASH_ROUNDS, H,
-         status);
+  LAUNCH(k_hash_tail, grid_for(threads), BN_BLOCK, msgs, (uint32_t)msg_len, (uint32_t)rounds, (uint32_t)cap, L[(rounds - 1) & 1], C + rounds, H, status);
   return 0;
 }
 
@@ -1102,24 +1324,40 @@ static int launch_coop_groups(bn254_ctx* ctx, int which, size_t n, size_t n_pad,
   return 0;
 }
 
-// msgs == NULL: check_public_keys form (first G1 argument = generator, no hashing)
+// msgs == NULL: check_public_keys form (first G1 argument = generator, no hashing; the caller has zeroed `status`)
 static int verify_dev_impl(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, const uint8_t* sigs, const uint8_t* pks, size_t n,
                            uint8_t* status, cudaEvent_t inputs_ready = nullptr) {
   const bool coop = ctx->pairing_mode != 1;
   const bool wl = ctx->pairing_mode == 3 || (ctx->pairing_mode == 0 && ctx->coop_w);
   const bool hl = !wl && (ctx->pairing_mode == 4 || (ctx->pairing_mode == 0 && ctx->coop_h));
-  // chunking bounds the workspace: the cooperative path stores 174 line sets (50 KB) per item, 55 GB for the default chunk of
-  // 2^20 items (of the 180 GB; BN254_COOP_CHUNK_LOG2 lowers it: 2^17-item chunks cost 1.1 % of the throughput)
+  // chunking bounds the workspace: the cooperative path stores 174 line sets (50 KB) per item, 27.5 GB for the default chunk of
+  // 2^19 items (BN254_COOP_CHUNK_LOG2 changes it; 2^20-item chunks are 0.4 % faster, 2^17-item chunks 1.1 % slower).  The
+  // workspace comes from the context's pool and stays cached there between calls; if the device cannot hold it the chunk is halved.
   // (warp-local layout: a whole number of waves of 30-item blocks, so that the last wave of a chunk is not mostly empty)
-  const size_t CHUNK = !coop ? ((size_t)1 << 20) : wl ? (size_t)ctx->sm_count * BN_COOP_MINB * COOPW_ITEMS * 7 : ((size_t)1 << ctx->chunk_log2);
-  size_t cap = n < CHUNK ? n : CHUNK;
-  size_t cap_pad = (cap + COOP_LANES - 1) / COOP_LANES * COOP_LANES;
+  size_t CHUNK = !coop ? ((size_t)1 << 20) : wl ? (size_t)ctx->sm_count * BN_COOP_MINB * COOPW_ITEMS * 7 : ((size_t)1 << ctx->chunk_log2);
   // the hash runs once over the whole batch: its compacting rounds are latency-bound when a round gets small, so one
   // pass over n items costs far less than n / CHUNK passes over CHUNK items
   DALLOC(H, sizeof(g1aff) * (msgs ? n : 1));
-  DALLOC(F, coop ? 16 : sizeof(fq12) * cap);
-  DALLOC(LN, coop ? sizeof(u4) * 2 * COOP_LINE_FQ * 2 * K_N_LINES * cap_pad : 16);
-  DALLOC(GS, coop ? sizeof(u4) * COOP_GSLOTS * 6 * 2 * 2 * cap_pad : 16);
+  dbuf F(ctx), LN(ctx), GS(ctx);
+  for (;;) {
+    size_t cap = n < CHUNK ? n : CHUNK;
+    size_t cap_pad = (cap + COOP_LANES - 1) / COOP_LANES * COOP_LANES;
+    cudaError_t e1 = F.alloc(coop ? 16 : sizeof(fq12) * cap);
+    cudaError_t e2 = e1 == cudaSuccess ? LN.alloc(coop ? sizeof(u4) * 2 * COOP_LINE_FQ * 2 * K_N_LINES * cap_pad : 16) : e1;
+    cudaError_t e3 = e2 == cudaSuccess ? GS.alloc(coop ? sizeof(u4) * COOP_GSLOTS * 6 * 2 * 2 * cap_pad : 16) : e2;
+    if (e3 == cudaSuccess) break;
+    cudaGetLastError();  // clear the allocation failure and retry with half the chunk
+    F.release();
+    LN.release();
+    GS.release();
+    if (e3 != cudaErrorMemoryAllocation || CHUNK <= 1024) {
+      ctx->err = std::string("verify workspace allocation failed: ") + cudaGetErrorString(e3);
+      return e3 == cudaErrorMemoryAllocation ? BN254_E_NOMEM : BN254_E_CUDA;
+    }
+    CHUNK >>= 1;
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemPoolTrimTo(ctx->pool, 0));  // give cached blocks of other shapes back before the retry
+  }
   for (size_t off = 0; off < n; off += CHUNK) {
     size_t m = n - off < CHUNK ? n - off : CHUNK;
     g1aff* h = nullptr;
@@ -1141,6 +1379,8 @@ static int verify_dev_impl(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, 
     }
     if (inputs_ready && off == 0) CK(cudaStreamWaitEvent(ctx->stream, inputs_ready, 0));  // sigs / pks arrive on the copy stream
     CK(mark());
+    if (ctx->input_policy == BN254_INPUTS_UNTRUSTED)
+      LAUNCH(k_validate_inputs, grid_for(m), BN_BLOCK, sigs + 64 * off, pks + 128 * off, m, status + off);
     if (coop) {
       size_t m_pad = (m + COOP_LANES - 1) / COOP_LANES * COOP_LANES;
       LAUNCH(k_verify_lines, grid_for(m), BN_BLOCK, h, sigs + 64 * off, pks + 128 * off, m, LN.as<u4>(), m_pad, status + off, ctx->d_lines);
@@ -1217,18 +1457,25 @@ int bn254_verify_batch(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, cons
   // uploaded on the copy stream while the hash kernels run, and the line-set kernel waits for them
   CK(cudaEventRecord(ctx->ev_alloc, ctx->stream));  // the buffers exist (stream-ordered allocation) from here on
   CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_alloc, 0));
-  CK(cudaMemcpyAsync(d_sigs.p, sigs, 64 * n, cudaMemcpyHostToDevice, ctx->copy_stream));
-  CK(cudaMemcpyAsync(d_pks.p, pks, 128 * n, cudaMemcpyHostToDevice, ctx->copy_stream));
-  CK(cudaEventRecord(ctx->ev_copy, ctx->copy_stream));
-  if (msg_len) H2D(d_msgs.p, msgs, msg_len * n);
-  int rc = verify_dev_impl(ctx, d_msgs.as<uint8_t>(), msg_len, d_sigs.as<uint8_t>(), d_pks.as<uint8_t>(), n, d_st.as<uint8_t>(), ctx->ev_copy);
+  // from here on copies may be in flight on the copy stream into buffers that the destructors free on the compute stream:
+  // every exit path first drains both streams
+  auto body = [&]() -> int {
+    CK(cudaMemcpyAsync(d_sigs.p, sigs, 64 * n, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CK(cudaMemcpyAsync(d_pks.p, pks, 128 * n, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CK(cudaEventRecord(ctx->ev_copy, ctx->copy_stream));
+    if (msg_len) H2D(d_msgs.p, msgs, msg_len * n);
+    int rc = verify_dev_impl(ctx, d_msgs.as<uint8_t>(), msg_len, d_sigs.as<uint8_t>(), d_pks.as<uint8_t>(), n, d_st.as<uint8_t>(), ctx->ev_copy);
+    if (rc) return rc;
+    D2H(status, d_st.p, n);
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+  };
+  int rc = body();
   if (rc) {
     cudaStreamSynchronize(ctx->copy_stream);
-    return rc;
+    cudaStreamSynchronize(ctx->stream);
   }
-  D2H(status, d_st.p, n);
-  CK(cudaStreamSynchronize(ctx->stream));
-  return 0;
+  return rc;
 }
 int bn254_check_public_keys_batch(bn254_ctx* ctx, const uint8_t* pk_g2, const uint8_t* pk_g1, size_t n, uint8_t* status) {
   ENTER();
@@ -1371,7 +1618,7 @@ static int item_op_host(bn254_ctx* ctx, const uint8_t* a, size_t a_bytes, const 
 }
 
 template <class F>
-static int sum_dev_impl(bn254_ctx* ctx, const uint8_t* pts, const uint8_t* neg, size_t n, uint8_t* out, uint8_t* status) {
+static int sum_dev_impl(bn254_ctx* ctx, const uint8_t* pts, const uint8_t* neg, size_t n, uint8_t* out, uint8_t* status, int strict = 0) {
   size_t want = (n + 7) / 8;  // >= 8 points per thread before the tree
   size_t max_blocks = (size_t)ctx->sm_count * 4;
   size_t blocks = (want + BN_BLOCK - 1) / BN_BLOCK;
@@ -1380,7 +1627,7 @@ static int sum_dev_impl(bn254_ctx* ctx, const uint8_t* pts, const uint8_t* neg, 
   DALLOC(partial, sizeof(jac<F>) * blocks);
   DALLOC(err, 8);
   CK(cudaMemsetAsync(err.p, 0xff, 8, ctx->stream));
-  LAUNCH(k_sum_partial<F>, (unsigned)blocks, BN_BLOCK, pts, neg, n, partial.as<jac<F>>(), err.as<unsigned long long>());
+  LAUNCH(k_sum_partial<F>, (unsigned)blocks, BN_BLOCK, pts, neg, n, partial.as<jac<F>>(), err.as<unsigned long long>(), strict);
   LAUNCH(k_sum_final<F>, 1, BN_BLOCK, partial.as<jac<F>>(), (int)blocks, out, err.as<unsigned long long>(), status);
   return 0;
 }
@@ -1402,64 +1649,114 @@ static int sum_host_impl(bn254_ctx* ctx, const uint8_t* pts, const uint8_t* neg,
   return 0;
 }
 
-// Miller-product partial of (H(msg_i), pk_i), i < n  ->  f_be (384 bytes, device) ; status = first error or 0
 struct dptr {  // a borrowed device pointer with the accessor of dbuf
   void* p;
   template <class T> T* as() { return (T*)p; }
 };
+// product of `count` Fq12 values on the device -> *f_be (384 bytes) and *status (first error by index, or 0); folds in
+// levels of 64 so that no single block multiplies more than a few thousand values in sequence
+static int fq12_product_dev(bn254_ctx* ctx, fq12* vals, size_t count, dbuf& scratch, uint8_t* f_be, unsigned long long* err, uint8_t* status) {
+  fq12* cur = vals;
+  size_t m = count;
+  fq12* sc = scratch.as<fq12>();
+  while (m > 4096) {
+    size_t per = 64, blocks = (m + per - 1) / per;
+    LAUNCH(k_fq12_prod_level, (unsigned)blocks, BN_PROD_BLOCK, cur, m, per, sc);
+    cur = sc;
+    sc += blocks;
+    m = blocks;
+  }
+  LAUNCH(k_fq12_prod_final, 1, BN_PROD_BLOCK, cur, (int)m, (fq12*)nullptr, f_be, err, status);
+  return 0;
+}
 // Miller-product partial of (P_i, pk_i), i < n, for G1 points already on the device (affine, Montgomery form; hst_p = their
-// per-item status)  ->  f_be (384 bytes, device) ; status = first error or 0
+// per-item status)  ->  f_be (384 bytes, device) ; status = first error or 0.  extra_sig (device, 64 bytes, may be NULL):
+// one more pair (extra_sig, -G2) is folded into the product.
 static int distinct_partial_points_dev(bn254_ctx* ctx, g1aff* H_p, uint8_t* hst_p, const uint8_t* pks, size_t n, uint8_t* f_be,
-                                       uint8_t* status) {
+                                       uint8_t* status, const uint8_t* extra_sig = nullptr) {
   dptr H{H_p}, hst{hst_p};
   DALLOC(err, 8);
   CK(cudaMemsetAsync(err.p, 0xff, 8, ctx->stream));
-  if (ctx->pairing_mode != 1 && n > 0) {
-    // cooperative multi-pairing: chunks of 2^20 pairs (26 GB of line sets), every block leaves one partial product
-    const size_t CH = (size_t)1 << 20;
-    const size_t per_block = (size_t)COOP_LANES * COOP_MULTI_K;
-    size_t total_blocks = 0;
-    for (size_t off = 0; off < n; off += CH) total_blocks += ((n - off < CH ? n - off : CH) + per_block - 1) / per_block;
-    size_t capn = n < CH ? n : CH;
-    size_t capL = (capn + per_block - 1) / per_block * COOP_LANES;
-    DALLOC(LN, sizeof(u4) * COOP_MULTI_K * COOP_LINE_FQ * 2 * K_N_LINES * capL);
-    DALLOC(FIO, sizeof(u4) * 6 * 2 * 2 * capL);
-    DALLOC(partial, sizeof(fq12) * total_blocks);
-    size_t done_blocks = 0;
-    for (size_t off = 0; off < n; off += CH) {
-      size_t m = n - off < CH ? n - off : CH;
-      size_t blocks = (m + per_block - 1) / per_block, L = blocks * COOP_LANES;
-      LAUNCH(k_pair_lines, grid_for(L * COOP_MULTI_K), BN_BLOCK, H.as<g1aff>() + off, hst.as<uint8_t>() + off, pks + 128 * off, m, L, LN.as<u4>(),
-             err.as<unsigned long long>(), off);
-      {
-        int rc2 = launch_coop_groups(ctx, 4, L, L, LN.as<u4>(), (u4*)nullptr, FIO.as<u4>(), (uint8_t*)nullptr, blocks);
-        if (rc2) return rc2;
-      }
-      LAUNCH(k_coop_gather, grid_for(blocks), BN_BLOCK, FIO.as<u4>(), L, blocks, partial.as<fq12>() + done_blocks);
-      done_blocks += blocks;
+  const int typed = ctx->input_policy == BN254_INPUTS_TYPED ? 1 : 0;
+  const size_t N = n + (extra_sig ? 1 : 0);  // pairs, the optional extra one last
+  if (ctx->pairing_mode != 1 && N > 0) {
+    // Cooperative multi-pairing.  A block of the default layout is four 32-lane groups, every lane folds mk pairs (shared
+    // squarings) and every group leaves one partial product.  Work is cut into launches of whole waves: full waves of
+    // mk = 8 blocks (1024 pairs each, at most 6 waves = 23 GB of line sets per launch), then ONE more wave for the
+    // remainder with the smallest mk in {8, 4, 2, 1} whose block count still fits a wave -- a partial last wave of
+    // mk = 8 blocks would cost a full wave's time (15 % of the step when 2^22 pairs are spread over 8 GPUs).
+    const size_t sms = (size_t)ctx->sm_count, gpb = (ctx->pairing_mode == 2 || !ctx->coop_groups4) ? 1 : COOP4_GROUPS;
+    struct seg { size_t off, cnt; int mk, prog; };
+    std::vector<seg> segs;
+    const size_t pairs_wave8 = sms * gpb * COOP_LANES * 8;
+    size_t full = N / pairs_wave8 * pairs_wave8;
+    for (size_t off = 0; off < full;) {
+      size_t c = full - off < 6 * pairs_wave8 ? full - off : 6 * pairs_wave8;
+      segs.push_back({off, c, 8, CPROG_MULTI8});
+      off += c;
     }
-    LAUNCH(k_fq12_prod_final, 1, BN_PROD_BLOCK, partial.as<fq12>(), (int)total_blocks, (fq12*)nullptr, f_be, err.as<unsigned long long>(), status);
-    return 0;
+    if (N > full) {
+      const size_t R = N - full;
+      int mk = 8, prog = CPROG_MULTI8;
+      const int mks[3] = {1, 2, 4}, progs[3] = {CPROG_MULTI1, CPROG_MULTI2, CPROG_MULTI4};
+      for (int t = 0; t < 3; t++)
+        if ((R + gpb * COOP_LANES * mks[t] - 1) / (gpb * COOP_LANES * mks[t]) <= sms) {
+          mk = mks[t];
+          prog = progs[t];
+          break;
+        }
+      segs.push_back({full, R, mk, prog});
+    }
+    size_t total_groups = 0, max_pairs_lanes = 0, maxL = 0;
+    for (auto& sg : segs) {
+      size_t groups = (sg.cnt + (size_t)COOP_LANES * sg.mk - 1) / ((size_t)COOP_LANES * sg.mk);
+      total_groups += groups;
+      size_t L = groups * COOP_LANES;
+      if (L * sg.mk > max_pairs_lanes) max_pairs_lanes = L * sg.mk;
+      if (L > maxL) maxL = L;
+    }
+    DALLOC(LN, sizeof(u4) * COOP_LINE_FQ * 2 * K_N_LINES * max_pairs_lanes);
+    DALLOC(FIO, sizeof(u4) * 6 * 2 * 2 * maxL);
+    DALLOC(partial, sizeof(fq12) * total_groups);
+    DALLOC(scratch, sizeof(fq12) * (total_groups / 32 + 64));
+    size_t done_groups = 0;
+    for (auto& sg : segs) {
+      size_t groups = (sg.cnt + (size_t)COOP_LANES * sg.mk - 1) / ((size_t)COOP_LANES * sg.mk), L = groups * COOP_LANES;
+      // pairs of this launch that come from the caller's arrays (the extra pair, if any, is the very last pair of all)
+      size_t own = sg.off + sg.cnt > n ? (n > sg.off ? n - sg.off : 0) : sg.cnt;
+      const uint8_t* ex = (extra_sig && sg.off + sg.cnt == N) ? extra_sig : nullptr;
+      LAUNCH(k_pair_lines, grid_for(L * sg.mk), BN_BLOCK, H.as<g1aff>() + sg.off, hst.as<uint8_t>() + sg.off, pks + 128 * sg.off, own, L, sg.mk,
+             LN.as<u4>(), err.as<unsigned long long>(), sg.off, ex, typed);
+      int rc2 = launch_coop_groups(ctx, sg.prog, L, L, LN.as<u4>(), (u4*)nullptr, FIO.as<u4>(), (uint8_t*)nullptr, groups);
+      if (rc2) return rc2;
+      LAUNCH(k_coop_gather, grid_for(groups), BN_BLOCK, FIO.as<u4>(), L, groups, partial.as<fq12>() + done_groups);
+      done_groups += groups;
+    }
+    return fq12_product_dev(ctx, partial.as<fq12>(), total_groups, scratch, f_be, err.as<unsigned long long>(), status);
   }
   size_t max_blocks = (size_t)ctx->sm_count * 4;
   size_t blocks = (n + BN_PROD_BLOCK - 1) / BN_PROD_BLOCK;
   if (blocks > max_blocks) blocks = max_blocks;
   if (blocks == 0) blocks = 1;
-  DALLOC(partial, sizeof(fq12) * blocks);
+  DALLOC(partial, sizeof(fq12) * (blocks + 1));
   LAUNCH(k_distinct_partial, (unsigned)blocks, BN_PROD_BLOCK, H.as<g1aff>(), hst.as<uint8_t>(), pks, n, partial.as<fq12>(),
-         err.as<unsigned long long>());
+         err.as<unsigned long long>(), typed);
+  if (extra_sig) {
+    LAUNCH(k_extra_pair, 1, 32, extra_sig, ctx->d_lines, partial.as<fq12>() + blocks, err.as<unsigned long long>(), n);
+    blocks++;
+  }
   LAUNCH(k_fq12_prod_final, 1, BN_PROD_BLOCK, partial.as<fq12>(), (int)blocks, (fq12*)nullptr, f_be, err.as<unsigned long long>(), status);
   return 0;
 }
 // Miller-product partial of (H(msg_i), pk_i), i < n  ->  f_be (384 bytes, device) ; status = first error or 0
 static int distinct_partial_dev(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, const uint8_t* pks, size_t n, uint8_t* f_be,
-                                uint8_t* status) {
+                                uint8_t* status, const uint8_t* extra_sig = nullptr) {
   size_t cap = n ? n : 1;
   DALLOC(H, sizeof(g1aff) * cap);
   DALLOC(hst, cap);
   int rc = hash_dev(ctx, msgs, msg_len, nullptr, n, H.as<g1aff>(), hst.as<uint8_t>(), nullptr);
   if (rc) return rc;
-  return distinct_partial_points_dev(ctx, H.as<g1aff>(), hst.as<uint8_t>(), pks, n, f_be, status);
+  return distinct_partial_points_dev(ctx, H.as<g1aff>(), hst.as<uint8_t>(), pks, n, f_be, status, extra_sig);
 }
 
 // ---- randomised batch verification (items.cuh item_rlc_prepare): fast path when every item rides, exact path otherwise
@@ -1495,9 +1792,9 @@ static int verify_rlc_dev_impl(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_l
     LAUNCH(k_rlc_prepare, grid_for(m), BN_BLOCK, H.as<g1aff>(), hst.as<uint8_t>(), cs, cp, coeffs16 + 16 * off, m, (flags & 1) ? 0 : 1,
            sigc.as<uint8_t>(), bad.as<unsigned>(), L, W);
     // pairs of items that cannot ride are harmless here (skipped or multiplied into a slice that is already marked)
-    LAUNCH(k_pair_lines, grid_for(L * COOP_MULTI_K), BN_BLOCK, H.as<g1aff>(), hst.as<uint8_t>(), cp, m, L, LN.as<u4>(),
-           err.as<unsigned long long>(), (size_t)0);
-    rc = launch_coop_groups(ctx, 4, L, L, LN.as<u4>(), (u4*)nullptr, FIO.as<u4>(), (uint8_t*)nullptr, groups);
+    LAUNCH(k_pair_lines, grid_for(L * COOP_MULTI_K), BN_BLOCK, H.as<g1aff>(), hst.as<uint8_t>(), cp, m, L, COOP_MULTI_K, LN.as<u4>(),
+           err.as<unsigned long long>(), (size_t)0, (const uint8_t*)nullptr, 1);
+    rc = launch_coop_groups(ctx, CPROG_MULTI8, L, L, LN.as<u4>(), (u4*)nullptr, FIO.as<u4>(), (uint8_t*)nullptr, groups);
     if (rc) return rc;
     LAUNCH(k_coop_gather, grid_for(groups), BN_BLOCK, FIO.as<u4>(), L, groups, partial.as<fq12>());
     LAUNCH(k_rlc_slice_sums, (unsigned)slices, BN_BLOCK, sigc.as<uint8_t>(), m, L, W, bad.as<unsigned>(), agg.as<uint8_t>());
@@ -1651,37 +1948,52 @@ int bn254_aggregate_verify_same_msg(bn254_ctx* ctx, const uint8_t* msg, size_t m
   DALLOC(d_msg, msg_len + 1);
   DALLOC(d_sigs, 64 * n);
   DALLOC(d_pks, 128 * n);
-  DALLOC(d_asig, 64);
-  DALLOC(d_apk, 128);
   DALLOC(d_st, 4);
   if (msg_len) H2D(d_msg.p, msg, msg_len);
   if (n) {
     H2D(d_sigs.p, sigs, 64 * n);
     H2D(d_pks.p, pks, 128 * n);
   }
-  uint8_t* st = d_st.as<uint8_t>();
-  int rc = sum_dev_impl<fq>(ctx, d_sigs.as<uint8_t>(), nullptr, n, d_asig.as<uint8_t>(), st + 0);
+  int rc = bn254_aggregate_verify_same_msg_dev(ctx, d_msg.as<uint8_t>(), msg_len, d_sigs.as<uint8_t>(), d_pks.as<uint8_t>(), n, d_st.as<uint8_t>());
   if (rc) return rc;
-  rc = sum_dev_impl<fq2>(ctx, d_pks.as<uint8_t>(), nullptr, n, d_apk.as<uint8_t>(), st + 1);
-  if (rc) return rc;
-  rc = verify_dev_impl(ctx, d_msg.as<uint8_t>(), msg_len, d_asig.as<uint8_t>(), d_apk.as<uint8_t>(), 1, st + 2);
-  if (rc) return rc;
-  uint8_t h[4] = {0, 0, 0, 0};
-  D2H(h, d_st.p, 3);
+  D2H(status, d_st.p, 1);
   CK(cudaStreamSynchronize(ctx->stream));
-  *status = h[0] ? h[0] : (h[1] ? h[1] : h[2]);
+  return 0;
+}
+// device form: sums + one verify, no host round trip; *status (device) = first failing stage (signature sum, key sum, verify)
+int bn254_aggregate_verify_same_msg_dev(bn254_ctx* ctx, const uint8_t* msg, size_t msg_len, const uint8_t* sigs, const uint8_t* pks, size_t n,
+                                        uint8_t* status) {
+  ENTER();
+  ARGCHECK(status != nullptr);
+  DALLOC(d_asig, 64);
+  DALLOC(d_apk, 128);
+  DALLOC(d_st, 4);
+  uint8_t* st = d_st.as<uint8_t>();
+  const int strict = ctx->input_policy == BN254_INPUTS_UNTRUSTED;
+  int rc = sum_dev_impl<fq>(ctx, sigs, nullptr, n, d_asig.as<uint8_t>(), st + 0, strict);
+  if (rc) return rc;
+  rc = sum_dev_impl<fq2>(ctx, pks, nullptr, n, d_apk.as<uint8_t>(), st + 1, strict);
+  if (rc) return rc;
+  // the sums are values of the crate's types (they may be infinity, and the key sum is in G2 because every key is)
+  const int saved = ctx->input_policy;
+  ctx->input_policy = BN254_INPUTS_TYPED;
+  rc = verify_dev_impl(ctx, msg, msg_len, d_asig.as<uint8_t>(), d_apk.as<uint8_t>(), 1, st + 2);
+  ctx->input_policy = saved;
+  if (rc) return rc;
+  LAUNCH(k_first_status, 1, 32, st, 3, status);
   return 0;
 }
 
 int bn254_miller_partial_distinct_dev(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, const uint8_t* pks, size_t n, uint8_t* f_out384,
                                       uint8_t* status) {
   ENTER();
+  ARGCHECK(f_out384 && status && (n == 0 || (pks && (msgs || msg_len == 0))));
   return distinct_partial_dev(ctx, msgs, msg_len, pks, n, f_out384, status);
 }
 int bn254_miller_partial_distinct(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, const uint8_t* pks, size_t n, uint8_t* f_out384,
                                   uint8_t* status) {
   ENTER();
-  ARGCHECK(f_out384 && status && (n == 0 || pks));
+  ARGCHECK(f_out384 && status && (n == 0 || (pks && (msgs || msg_len == 0))));
   DALLOC(d_msgs, msg_len * n + 1);
   DALLOC(d_pks, 128 * n);
   DALLOC(d_f, 384);
@@ -1695,29 +2007,115 @@ int bn254_miller_partial_distinct(bn254_ctx* ctx, const uint8_t* msgs, size_t ms
   CK(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
+// One rank's share of a distinct-message aggregate check as ONE fixed-size device record (BN254_DISTINCT_PAYLOAD_BYTES): the
+// Miller product of its (H(msg_i), pk_i) pairs and -- when sigs != NULL -- of the pair (sum of its signatures, -G2), plus the
+// status byte.  The records of all ranks are exchanged (all-gather straight into a device buffer) and bn254_finish_distinct_dev
+// folds them; with sigs given on every rank no signature material has to travel at all.
+int bn254_distinct_payload_dev(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, const uint8_t* pks, const uint8_t* sigs, size_t n,
+                               uint8_t* payload) {
+  ENTER();
+  ARGCHECK(payload && (n == 0 || (pks && (msgs || msg_len == 0))));
+  CK(cudaMemsetAsync(payload, 0, BN_PAYLOAD, ctx->stream));
+  if (!sigs) return distinct_partial_dev(ctx, msgs, msg_len, pks, n, payload, payload + 384);
+  DALLOC(d_sum, 64);
+  int rc = sum_dev_impl<fq>(ctx, sigs, nullptr, n, d_sum.as<uint8_t>(), payload + 386, ctx->input_policy == BN254_INPUTS_UNTRUSTED);
+  if (rc) return rc;
+  rc = distinct_partial_dev(ctx, msgs, msg_len, pks, n, payload, payload + 385, d_sum.as<uint8_t>());
+  if (rc) return rc;
+  LAUNCH(k_first_status, 1, 32, payload + 385, 2, payload + 384);
+  return 0;
+}
+// payloads: m records of BN254_DISTINCT_PAYLOAD_BYTES (device); agg_sig: 64 bytes (device) or NULL when every record already
+// holds its rank's signature pair.  *status (device) = first failing record's status, else the verdict.
+static int finish_payloads_dev(bn254_ctx* ctx, const uint8_t* payloads, size_t m, const uint8_t* agg_sig, uint8_t* status) {
+  if (ctx->pairing_mode == 1) {
+    LAUNCH(k_distinct_finish, 1, 32, payloads, (int)m, agg_sig, ctx->d_lines, status);
+    return 0;
+  }
+  // one item through the cooperative machine (six warps of one block): Miller loop over the 87 scaled -G2 lines of agg_sig,
+  // times the product of the records, final exponentiation, verdict
+  DALLOC(LNf, sizeof(u4) * COOP_LINE_FQ * 2 * K_N_LINES * COOP_LANES);
+  DALLOC(FIOf, sizeof(u4) * 6 * 2 * 2 * COOP_LANES);
+  DALLOC(GSf, sizeof(u4) * COOP_GSLOTS * 6 * 2 * 2 * COOP_LANES);
+  LAUNCH(k_finish_prepare, 1, BN_BLOCK, payloads, (int)m, agg_sig, ctx->d_lines, LNf.as<u4>(), FIOf.as<u4>(), status);
+  k_coop_run<<<1, COOP_THREADS, COOP_SMEM_BYTES, ctx->stream>>>(CPROG_FINISH, (size_t)1, (size_t)COOP_LANES, LNf.as<u4>(), GSf.as<u4>(), FIOf.as<u4>(), status,
+                                                                0u, (unsigned)ctx->sm_count);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+int bn254_finish_distinct_dev(bn254_ctx* ctx, const uint8_t* payloads, size_t n_payloads, const uint8_t* agg_sig, uint8_t* status) {
+  ENTER();
+  ARGCHECK(status && (n_payloads == 0 || payloads) && n_payloads <= 0x7fffff);
+  return finish_payloads_dev(ctx, payloads, n_payloads, agg_sig, status);
+}
 int bn254_finish_distinct(bn254_ctx* ctx, const uint8_t* partials384, size_t n_partials, const uint8_t* agg_sig, uint8_t* status) {
   ENTER();
-  ARGCHECK(status && agg_sig && (n_partials == 0 || partials384));
-  DALLOC(d_p, 384 * n_partials);
+  ARGCHECK(status && agg_sig && (n_partials == 0 || partials384) && n_partials <= 0x7fffff);
+  std::vector<uint8_t> host(BN_PAYLOAD * (n_partials ? n_partials : 1), 0);
+  for (size_t i = 0; i < n_partials; i++) memcpy(&host[BN_PAYLOAD * i], partials384 + 384 * i, 384);
+  DALLOC(d_p, host.size());
   DALLOC(d_sig, 64);
   DALLOC(d_st, 1);
-  if (n_partials) H2D(d_p.p, partials384, 384 * n_partials);
+  H2D(d_p.p, host.data(), host.size());
   H2D(d_sig.p, agg_sig, 64);
-  LAUNCH(k_distinct_finish, 1, 32, d_p.as<uint8_t>(), (int)n_partials, d_sig.as<uint8_t>(), ctx->d_lines, d_st.as<uint8_t>());
+  int rc = finish_payloads_dev(ctx, d_p.as<uint8_t>(), n_partials, d_sig.as<uint8_t>(), d_st.as<uint8_t>());
+  if (rc) {
+    cudaStreamSynchronize(ctx->stream);  // `host` is the source of an enqueued copy
+    return rc;
+  }
   D2H(status, d_st.p, 1);
   CK(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
 int bn254_aggregate_verify_distinct(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, const uint8_t* pks, size_t n, const uint8_t* agg_sig,
                                     uint8_t* status) {
-  uint8_t f[384], st = 0;
-  int rc = bn254_miller_partial_distinct(ctx, msgs, msg_len, pks, n, f, &st);
+  ENTER();
+  ARGCHECK(status && agg_sig && (n == 0 || (pks && (msgs || msg_len == 0))));
+  DALLOC(d_msgs, msg_len * n + 1);
+  DALLOC(d_pks, 128 * n + 1);
+  DALLOC(d_sig, 64);
+  DALLOC(d_pl, BN_PAYLOAD);
+  DALLOC(d_st, 1);
+  if (n && msg_len) H2D(d_msgs.p, msgs, msg_len * n);
+  if (n) H2D(d_pks.p, pks, 128 * n);
+  H2D(d_sig.p, agg_sig, 64);
+  int rc = bn254_distinct_payload_dev(ctx, d_msgs.as<uint8_t>(), msg_len, d_pks.as<uint8_t>(), nullptr, n, d_pl.as<uint8_t>());
   if (rc) return rc;
-  if (st) {
-    *status = st;
-    return 0;
-  }
-  return bn254_finish_distinct(ctx, f, 1, agg_sig, status);
+  rc = finish_payloads_dev(ctx, d_pl.as<uint8_t>(), 1, d_sig.as<uint8_t>(), d_st.as<uint8_t>());
+  if (rc) return rc;
+  D2H(status, d_st.p, 1);
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// format_pairing_check_values / format_pairing_check_uncompressed_values (/root/reference/src/utils.rs:197-239): per item
+// [(H(msg) 64 B, pk 128 B), (sig 64 B, -G2 128 B)] = 384 bytes, every 32-byte coordinate LITTLE-endian (the dependency's Borsh
+// form).  compressed != 0: sig is 33 bytes, pk 65 bytes, both decoded (and validated) like Signature / PublicKey::from_compressed;
+// compressed == 0: 64 / 128 bytes, re-ordered without validation exactly like the reference (:218-239).
+int bn254_format_pairing_check_batch(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, const uint8_t* sigs, const uint8_t* pks, size_t n,
+                                     int compressed, uint8_t* out384, uint8_t* status) {
+  ENTER();
+  if (n == 0) return 0;
+  ARGCHECK((msgs || msg_len == 0) && sigs && pks && out384 && status);
+  const size_t sb = compressed ? 33 : 64, pb = compressed ? 65 : 128;
+  DALLOC(d_msgs, msg_len * n + 1);
+  DALLOC(d_sigs, sb * n);
+  DALLOC(d_pks, pb * n);
+  DALLOC(H, sizeof(g1aff) * n);
+  DALLOC(d_out, 384 * n);
+  DALLOC(d_st, n);
+  if (msg_len) H2D(d_msgs.p, msgs, msg_len * n);
+  H2D(d_sigs.p, sigs, sb * n);
+  H2D(d_pks.p, pks, pb * n);
+  int rc = hash_dev(ctx, d_msgs.as<uint8_t>(), msg_len, nullptr, n, H.as<g1aff>(), d_st.as<uint8_t>(), nullptr);
+  if (rc) return rc;
+  LAUNCH(k_format_pairing_check, grid_for(n), BN_BLOCK, H.as<g1aff>(), d_sigs.as<uint8_t>(), d_pks.as<uint8_t>(), n, compressed, d_out.as<uint8_t>(),
+         d_st.as<uint8_t>());
+  D2H(out384, d_out.p, 384 * n);
+  D2H(status, d_st.p, n);
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
 }
 
 }  // extern "C"

@@ -120,9 +120,9 @@ BN_FN int item_verify_lines(u4* lines, size_t n_pad, size_t item, const g1aff* h
 }
 
 // Multi-pairing producer: pair (h, pk) is stream `stream` of its lane `item`; its 87 line sets go to set index
-// step * COOP_MULTI_K + stream.  use == false (padding slot, pk at infinity, or an item that failed to decode) writes the
+// step * mk + stream (mk = pairs per lane of the program that will consume them).  use == false (padding slot, pk at infinity, or an item that failed to decode) writes the
 // constant 1 everywhere, which leaves the lane's product unchanged.
-BN_FN void item_pair_lines(u4* lines, size_t n_pad, size_t item, int stream, bool use, const g1aff* h, const fq2& qx, const fq2& qy,
+BN_FN void item_pair_lines(u4* lines, size_t n_pad, size_t item, int stream, int mk, bool use, const g1aff* h, const fq2& qx, const fq2& qy,
                            lines_consts* K) {
   K->v[0] = qx;
   K->v[1] = qy;
@@ -136,22 +136,22 @@ BN_FN void item_pair_lines(u4* lines, size_t n_pad, size_t item, int stream, boo
 #pragma unroll 1
   for (int k = 0; k < 64; k++) {
     if (use) doubling_step_v(rx, ry, rz, c0, cvw, cvv);
-    coop_emit_scaled_v(lines, m * COOP_MULTI_K + stream, n_pad, item, use, c0, cvw, cvv, K->v[2]);
+    coop_emit_scaled_v(lines, m * mk + stream, n_pad, item, use, c0, cvw, cvv, K->v[2]);
     m++;
     const int d = K_ATE_DIGITS[k];
     if (d != 0) {
       if (use) mixed_addition_step_v(K->v[0], d > 0 ? K->v[1] : fq2_neg(K->v[1]), rx, ry, rz, c0, cvw, cvv);
-      coop_emit_scaled_v(lines, m * COOP_MULTI_K + stream, n_pad, item, use, c0, cvw, cvv, K->v[2]);
+      coop_emit_scaled_v(lines, m * mk + stream, n_pad, item, use, c0, cvw, cvv, K->v[2]);
       m++;
     }
   }
   fq2 q1x, q1y, q2x, q2y;
   g2_frobenius_pair(&q1x, &q1y, &q2x, &q2y, K->v[0], K->v[1]);
   if (use) mixed_addition_step_v(q1x, q1y, rx, ry, rz, c0, cvw, cvv);
-  coop_emit_scaled_v(lines, m * COOP_MULTI_K + stream, n_pad, item, use, c0, cvw, cvv, K->v[2]);
+  coop_emit_scaled_v(lines, m * mk + stream, n_pad, item, use, c0, cvw, cvv, K->v[2]);
   m++;
   if (use) mixed_addition_step_v(q2x, q2y, rx, ry, rz, c0, cvw, cvv);
-  coop_emit_scaled_v(lines, m * COOP_MULTI_K + stream, n_pad, item, use, c0, cvw, cvv, K->v[2]);
+  coop_emit_scaled_v(lines, m * mk + stream, n_pad, item, use, c0, cvw, cvv, K->v[2]);
 }
 
 }  // namespace bn

@@ -114,7 +114,9 @@ BN_FN int item_verify_miller(fq12* f, const g1aff* h, const uint8_t* sig, const 
 // final exponentiation and comparison with one (/root/reference/src/ecdsa.rs:59-63)
 BN_FN uint8_t item_final_exp_is_one(const fq12* f) {
   fq12 gt;
-  if (!final_exponentiation(&gt, f)) return ST_OK;  // unreachable for valid inputs; the oracle maps it to one
+  // f == 0 cannot come out of a Miller loop over points of the curve; bn::pairing_batch would panic on it.  Fail closed, like
+  // the cooperative machine does (its Fermat inversion maps 0 to 0, which is not one).
+  if (!final_exponentiation(&gt, f)) return ST_VERIFICATION_FAILED;
   return fq12_is_one(&gt) ? ST_OK : ST_VERIFICATION_FAILED;
 }
 // Miller product of k generic pairs (bn::pairing_batch before the final exponentiation); pairs with an infinity are skipped

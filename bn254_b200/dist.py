@@ -1,10 +1,16 @@
-"""Multi-GPU host logic: one process per GPU (torch.distributed), shards of independent items, and the single exchange
-step the path has -- the all-gather of one 384-byte Miller product per rank for the distinct-message aggregate verify
-(SURVEY.md 8e).  Everything else (batch verify, sign, hash) is embarrassingly parallel: ranks take index ranges and
-no data-path collective runs.
+"""Multi-GPU host logic: one process per GPU (torch.distributed), shards of independent items, and the exchange steps the
+path has:
 
-The compute callbacks default to the CUDA engine; the CPU tests (`gloo`, world_size 2) inject the oracle instead, so
-that the sharding / exchange logic is covered on a machine without a GPU.
+  * distinct-message aggregate verify: every rank folds its slice into ONE fixed-size record (Miller product + status),
+    one all-gather of those records, then the single shared final exponentiation on every rank;
+  * same-message aggregate verify: per-rank partial G1 / G2 sums, one all-gather of 64 + 128 bytes (+ status), the last
+    additions and one verify on every rank.
+
+Everything else (batch verify, sign, hash) is embarrassingly parallel: ranks take index ranges and no data-path collective
+runs.  The `*_dev` functions keep every byte on the GPU: inputs are CUDA uint8 tensors, the collective is NCCL straight
+between device buffers, the finish kernels read the gathered buffer -- the only host read is the final status byte.  The
+byte-string functions take compute callbacks that default to the CUDA engine; the CPU tests (`gloo`, world_size 2) inject
+the oracle instead, so the sharding / exchange logic is covered on a machine without a GPU.
 """
 import torch
 import torch.distributed as dist
@@ -71,3 +77,118 @@ def aggregate_verify_distinct_sharded(msgs, msg_len, pks, agg_sig, partial_fn=No
         if p[384]:
             return p[384]
     return finish_fn(b"".join(p[:384] for p in parts), agg_sig)
+
+
+def aggregate_verify_same_msg_sharded(msg, sigs, pks, sum_g1_fn=None, sum_g2_fn=None, verify_fn=None, group=None):
+    """The flow of /root/reference/examples/bn254.rs:25-32 over sharded keys: every rank sums ITS signatures (G1) and ITS public
+    keys (G2), one all-gather of (64 + 128 + 2 status) bytes per rank, then the world-size additions and ONE verify of
+    (msg, sum of signatures, sum of keys) on every rank.  `sigs` / `pks` are this rank's slices.  Returns the status byte.
+    The sums are points in affine form, so the result does not depend on how the items were split."""
+    if sum_g1_fn is None or sum_g2_fn is None or verify_fn is None:
+        from . import engine
+        sum_g1_fn = sum_g1_fn or (lambda pts: engine.g1_sum(pts))
+        sum_g2_fn = sum_g2_fn or (lambda pts: engine.g2_sum(pts))
+        # the gathered sums are values of the crate's types (possibly infinity): verified under the typed policy
+        verify_fn = verify_fn or (lambda m, s, p: _typed_verify(m, s, p))
+    s1, st1 = sum_g1_fn(sigs)
+    s2, st2 = sum_g2_fn(pks)
+    parts = all_gather_bytes(s1 + s2 + bytes([st1, st2]), group)
+    for p in parts:
+        if p[192] or p[193]:
+            return p[192] or p[193]
+    a1, st = sum_g1_fn(b"".join(p[:64] for p in parts))
+    if st:
+        return st
+    a2, st = sum_g2_fn(b"".join(p[64:192] for p in parts))
+    if st:
+        return st
+    return verify_fn(msg, a1, a2)
+
+
+def _typed_verify(msg, sig, pk):
+    from . import engine
+    ctx = engine.context(torch.cuda.current_device())
+    engine.set_input_policy(engine.INPUTS_TYPED, ctx=ctx)
+    try:
+        return engine.verify_batch(msg if len(msg) else None, len(msg), sig, pk, ctx=ctx)[0]
+    finally:
+        engine.set_input_policy(engine.INPUTS_UNTRUSTED, ctx=ctx)
+
+
+# ---------------------------------------------------------------------------------------------- device-resident forms (NCCL)
+class DistinctAggregate:
+    """Distinct-message aggregate verify with every buffer on the GPU (BASELINE.json configs[4]).
+
+    step(msgs, pks, sigs) with this rank's slices as CUDA uint8 tensors:
+        bn254_distinct_payload_dev  -> one 448-byte record (Miller product of the rank's (H(m_i), pk_i) pairs AND of the pair
+                                       (sum of its signatures, -G2), status byte)
+        dist.all_gather_into_tensor -> world x 448 bytes, device to device over NVLink
+        bn254_finish_distinct_dev   -> product of the records, ONE final exponentiation (cooperative machine), verdict
+    Nothing is read back until status() copies the single verdict byte.  The record is 448 bytes per rank -- pure latency --
+    so the exchange is the library collective, not a fused kernel."""
+
+    def __init__(self, ctx, world=None, group=None):
+        from ._native import S
+        self.ctx, self.group, self._S = ctx, group, S
+        self.world = world if world is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
+        dev = torch.device("cuda", ctx.device)
+        self.payload = torch.zeros(448, dtype=torch.uint8, device=dev)
+        self.gathered = torch.zeros(448 * self.world, dtype=torch.uint8, device=dev)
+        self.verdict = torch.zeros(1, dtype=torch.uint8, device=dev)
+        self.stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    def step(self, msgs, msg_len, pks, sigs, n, agg_sig=None):
+        S = self._S
+        self.ctx.call("bn254_distinct_payload_dev", msgs, S(msg_len), pks, sigs, S(n), self.payload)
+        if self.world > 1:
+            with torch.cuda.stream(self.stream):  # the collective is ordered on the engine's stream: no host synchronisation
+                dist.all_gather_into_tensor(self.gathered, self.payload, group=self.group)
+            src = self.gathered
+        else:
+            src = self.payload
+        self.ctx.call("bn254_finish_distinct_dev", src, S(self.world), agg_sig, self.verdict)
+
+    def status(self):
+        self.ctx.sync()
+        return int(self.verdict.cpu()[0])
+
+
+class SameMessageAggregate:
+    """Same-message aggregate verify over sharded keys, device-resident: per-rank G1 / G2 sums (bn254_g{1,2}_sum_dev), one
+    all-gather of 256 bytes per rank, then bn254_aggregate_verify_same_msg_dev over the `world` partial sums.  The points are
+    values of the crate's types (validate bytes from outside first, bn254_g{1,2}_validate_batch): the context must be in
+    BN254_INPUTS_TYPED, because a partial sum may legitimately be the point at infinity."""
+
+    def __init__(self, ctx, world=None, group=None):
+        from ._native import S
+        assert ctx.input_policy == 1, "SameMessageAggregate needs a context with the typed input policy"
+        self.ctx, self.group, self._S = ctx, group, S
+        self.world = world if world is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
+        dev = torch.device("cuda", ctx.device)
+        self.rec = torch.zeros(256, dtype=torch.uint8, device=dev)        # [0,64) sig sum | [64,192) key sum | [192] [193] statuses
+        self.gathered = torch.zeros(256 * self.world, dtype=torch.uint8, device=dev)
+        self.sig_parts = torch.zeros(64 * self.world, dtype=torch.uint8, device=dev)
+        self.pk_parts = torch.zeros(128 * self.world, dtype=torch.uint8, device=dev)
+        self.verdict = torch.zeros(1, dtype=torch.uint8, device=dev)
+        self.stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    def step(self, msg, msg_len, sigs, pks, n):
+        S, w = self._S, self.world
+        self.ctx.call("bn254_g1_sum_dev", sigs, None, S(n), self.rec[0:64], self.rec[192:193])
+        self.ctx.call("bn254_g2_sum_dev", pks, None, S(n), self.rec[64:192], self.rec[193:194])
+        with torch.cuda.stream(self.stream):
+            if w > 1:
+                dist.all_gather_into_tensor(self.gathered, self.rec, group=self.group)
+            else:
+                self.gathered.copy_(self.rec)
+            g = self.gathered.view(w, 256)
+            self.sig_parts.copy_(g[:, 0:64].reshape(-1))
+            self.pk_parts.copy_(g[:, 64:192].reshape(-1))
+            self.part_status = g[:, 192:194].max()
+        self.ctx.call("bn254_aggregate_verify_same_msg_dev", msg, S(msg_len), self.sig_parts, self.pk_parts, S(w), self.verdict)
+
+    def status(self):
+        self.ctx.sync()
+        torch.cuda.synchronize()
+        ps = int(self.part_status.cpu())
+        return ps if ps else int(self.verdict.cpu()[0])

@@ -6,6 +6,9 @@ Statuses are one byte per item: 0 = Ok, otherwise the Error variant of /root/ref
 from ._native import Context, S, I, out
 
 _default = {}
+# bn254_set_input_policy (include/bn254_b200.h): how verify / check_public_keys / the aggregate checks read their point bytes
+INPUTS_UNTRUSTED, INPUTS_TYPED = 0, 1
+DISTINCT_PAYLOAD_BYTES = 448
 
 
 def context(device=0):
@@ -14,6 +17,17 @@ def context(device=0):
     if c is None:
         c = _default[device] = Context(device)
     return c
+
+
+def set_input_policy(policy, ctx=None):
+    """INPUTS_UNTRUSTED (default): signatures / keys are decoded like from_uncompressed (no infinity, G2 r-torsion test);
+    INPUTS_TYPED: values of the crate's types (all-zero bytes = infinity, membership trusted)."""
+    (ctx or context()).call("bn254_set_input_policy", I(policy))
+
+
+def set_hash_try_limit(max_tries, ctx=None):
+    """Test hook: counters tried by hash_to_try_and_increment (255 in the reference)."""
+    (ctx or context()).call("bn254_set_hash_try_limit", I(max_tries))
 
 
 def _n(buf, size):
@@ -41,9 +55,15 @@ def hash_to_g1_var(msgs_list, ctx=None):
     return o.raw[:64 * n], st.raw[:n], tr.raw[:n]
 
 
+def _msgs_ok(msgs, msg_len, n):
+    assert (len(msgs) if msgs is not None else 0) == msg_len * n, "messages: %d bytes, expected %d x %d" % (
+        len(msgs) if msgs is not None else 0, n, msg_len)
+
+
 def sign_batch(msgs, msg_len, sks, ctx=None):
     ctx = ctx or context()
     n = _n(sks, 32)
+    _msgs_ok(msgs, msg_len, n)
     o, st = out(64 * n), out(n)
     ctx.call("bn254_sign_batch", msgs, S(msg_len), sks, S(n), o, st)
     return o.raw[:64 * n], st.raw[:n]
@@ -56,6 +76,7 @@ def verify_batch_rlc(msgs, msg_len, sigs, pks, coeffs16=None, pks_in_g2=False, c
     ctx = ctx or context()
     n = _n(sigs, 64)
     assert _n(pks, 128) == n and (coeffs16 is None or len(coeffs16) == 16 * n)
+    _msgs_ok(msgs, msg_len, n)
     st, fast = out(n), ctypes.c_int(0)
     ctx.call("bn254_verify_batch_rlc", msgs, S(msg_len), sigs, pks, S(n), coeffs16, I(1 if pks_in_g2 else 0), st, fast)
     return st.raw[:n], bool(fast.value)
@@ -65,6 +86,7 @@ def verify_batch(msgs, msg_len, sigs, pks, ctx=None):
     ctx = ctx or context()
     n = _n(sigs, 64)
     assert _n(pks, 128) == n
+    _msgs_ok(msgs, msg_len, n)
     st = out(n)
     ctx.call("bn254_verify_batch", msgs, S(msg_len), sigs, pks, S(n), st)
     return st.raw[:n]
@@ -234,6 +256,18 @@ def finish_distinct(partials, agg_sig, ctx=None):
     st = out(1)
     ctx.call("bn254_finish_distinct", partials if n else None, S(n), agg_sig, st)
     return st.raw[0]
+
+
+def format_pairing_check_batch(msgs, msg_len, sigs, pks, compressed, ctx=None):
+    """format_pairing_check_values (compressed=True: 33-byte sigs, 65-byte pks) / _uncompressed_values (64 / 128 bytes):
+    -> (n x 384 bytes [(H(m), pk), (sig, -G2)] with little-endian coordinates, statuses)"""
+    ctx = ctx or context()
+    n = _n(sigs, 33 if compressed else 64)
+    assert _n(pks, 65 if compressed else 128) == n
+    _msgs_ok(msgs, msg_len, n)
+    o, st = out(384 * n), out(n)
+    ctx.call("bn254_format_pairing_check_batch", msgs, S(msg_len), sigs, pks, S(n), I(1 if compressed else 0), o, st)
+    return o.raw[:384 * n], st.raw[:n]
 
 
 def layer_op_batch(op, data, n_in, n_out, ctx=None):

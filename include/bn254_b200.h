@@ -17,6 +17,8 @@
  *   - Functions return 0 on success or a negative BN254_E_* engine error (CUDA failure, bad argument); the
  *     message is available from bn254_last_error().  There is no CPU fallback: without a CUDA device
  *     bn254_ctx_create fails.
+ *   - verify / check_public_keys / aggregate entry points validate their point inputs by default (BN254_INPUTS_UNTRUSTED below);
+ *     callers that hold values of the crate's types switch the context to BN254_INPUTS_TYPED.
  *   - Entry points without a suffix take HOST buffers and include the host<->device copies; the *_dev variants
  *     take DEVICE pointers (4-byte aligned), enqueue on the context's stream and return without synchronising
  *     (call bn254_sync).  A context is bound to one GPU; calls on one context must not overlap.
@@ -50,6 +52,22 @@ enum {
 /* engine-level errors (function return values) */
 enum { BN254_E_CUDA = -1, BN254_E_ARG = -2, BN254_E_NOMEM = -3 };
 
+/* How the G1 / G2 byte inputs of verify, check_public_keys and the aggregate checks are read (bn254_set_input_policy).
+ *   BN254_INPUTS_UNTRUSTED (default): bytes from outside.  Every signature / key is decoded exactly as
+ *     Signature::from_uncompressed / PublicKey::from_uncompressed decode it (/root/reference/src/utils.rs:107-127, which end in
+ *     AffineG1::new / AffineG2::new): field membership -> NotMemberError, curve equation -> InvalidGroupPoint -- all-zero bytes,
+ *     the engine's encoding of infinity, are (0, 0) and fail here -- and, for G2, the r-torsion test -> InvalidGroupPoint.
+ *     pk is decoded first, then sig; a decode error takes precedence over a hash error.
+ *   BN254_INPUTS_TYPED: the bytes are values of the crate's types (made by its constructors and + - operators): all-zero bytes are
+ *     the point at infinity, which bn::pairing_batch skips (so sig = infinity with pk = infinity VERIFIES, as in the crate), and G2
+ *     membership is a type invariant that is not re-checked.  The Rust wrapper uses this; never feed network bytes this way.
+ * The sum / pairing / codec building blocks always take typed values. */
+enum { BN254_INPUTS_UNTRUSTED = 0, BN254_INPUTS_TYPED = 1 };
+
+/* size of one rank's record of a distinct-message aggregate check (bn254_distinct_payload_dev): bytes [0, 384) the Miller
+ * product (12 x 32 B big-endian, tower order), byte 384 the status, the rest reserved */
+#define BN254_DISTINCT_PAYLOAD_BYTES 448
+
 typedef struct bn254_ctx bn254_ctx;
 
 /* lifecycle: one context per GPU; owns a stream, the -G2 line table, comb tables and the workspace */
@@ -60,6 +78,15 @@ int bn254_sync(bn254_ctx* ctx);
 void* bn254_stream(bn254_ctx* ctx);            /* the cudaStream_t used by every launch of this context */
 int bn254_sm_count(bn254_ctx* ctx);
 uint64_t bn254_launch_count(bn254_ctx* ctx);   /* kernels launched by this context so far */
+/* Temporaries (the 27 GB line-set workspace of a 2^19-item verify chunk included) come from a pool private to the context and stay
+ * cached there between calls; bn254_trim returns the cached memory to the driver (bn254_ctx_destroy does too).  If the device
+ * cannot hold the workspace, verify halves its chunk until it fits. */
+int bn254_trim(bn254_ctx* ctx);
+int bn254_set_input_policy(bn254_ctx* ctx, int policy);
+int bn254_get_input_policy(bn254_ctx* ctx);
+/* test hook: number of counters hash_to_try_and_increment tries (255 in the reference, /root/reference/src/hash.rs:39); lowering
+ * it is the only way to reach HashToPointError (/root/reference/src/hash.rs:62), whose natural probability is 2^-235 */
+int bn254_set_hash_try_limit(bn254_ctx* ctx, int max_tries);
 
 /* measurement support: when on, the verify pipeline brackets its three kernels (hash, Miller loop, final
  * exponentiation) with CUDA events on the context's stream; bn254_phase_ms returns and clears the accumulated times */
@@ -140,6 +167,8 @@ int bn254_g2_validate_batch(bn254_ctx*, const uint8_t* raw128, size_t n, uint8_t
  * then one verify of (msg, sum_sig, sum_pk) */
 int bn254_aggregate_verify_same_msg(bn254_ctx*, const uint8_t* msg, size_t msg_len, const uint8_t* sigs, const uint8_t* pks, size_t n,
                                     uint8_t* status);
+int bn254_aggregate_verify_same_msg_dev(bn254_ctx*, const uint8_t* msg, size_t msg_len, const uint8_t* sigs, const uint8_t* pks, size_t n,
+                                        uint8_t* status);
 /* distinct-message aggregate verify: prod_i e(H(msg_i), pk_i) * e(agg_sig, -G2) == 1, one shared final exponentiation */
 int bn254_aggregate_verify_distinct(bn254_ctx*, const uint8_t* msgs, size_t msg_len, const uint8_t* pks, size_t n, const uint8_t* agg_sig,
                                     uint8_t* status);
@@ -150,6 +179,21 @@ int bn254_miller_partial_distinct(bn254_ctx*, const uint8_t* msgs, size_t msg_le
 int bn254_miller_partial_distinct_dev(bn254_ctx*, const uint8_t* msgs, size_t msg_len, const uint8_t* pks, size_t n, uint8_t* f_out384,
                                       uint8_t* status);
 int bn254_finish_distinct(bn254_ctx*, const uint8_t* partials384, size_t n_partials, const uint8_t* agg_sig, uint8_t* status);
+/* the same exchange without leaving the device: every rank reduces its slice to ONE record of BN254_DISTINCT_PAYLOAD_BYTES
+ * (with sigs != NULL the pair (sum of the rank's signatures, -G2) is folded into the rank's Miller product, so no signature
+ * has to travel: prod_r e(S_r, -G2) = e(sum_r S_r, -G2)); the records are all-gathered into one device buffer and
+ * bn254_finish_distinct_dev multiplies them, adds the pair (agg_sig, -G2) when agg_sig != NULL, and runs the single final
+ * exponentiation through the cooperative machine.  *status (device, 1 byte) = first failing record's status, else the verdict. */
+int bn254_distinct_payload_dev(bn254_ctx*, const uint8_t* msgs, size_t msg_len, const uint8_t* pks, const uint8_t* sigs, size_t n,
+                               uint8_t* payload);
+int bn254_finish_distinct_dev(bn254_ctx*, const uint8_t* payloads, size_t n_payloads, const uint8_t* agg_sig, uint8_t* status);
+
+/* format_pairing_check_values (compressed != 0: 33-byte sig, 65-byte pk, decoded like from_compressed) and
+ * format_pairing_check_uncompressed_values (compressed == 0: 64 / 128 bytes, re-ordered without validation, as the reference does)
+ * (/root/reference/src/utils.rs:197-239): per item [(H(msg), pk), (sig, -G2)] = 64 + 128 + 64 + 128 bytes, every 32-byte
+ * coordinate little-endian (the dependency's Borsh form).  Errors in the reference's order: hash, public key, signature. */
+int bn254_format_pairing_check_batch(bn254_ctx*, const uint8_t* msgs, size_t msg_len, const uint8_t* sigs, const uint8_t* pks, size_t n,
+                                     int compressed, uint8_t* out384, uint8_t* status);
 
 /* building blocks exposed for parity tests and profiling of the two pairing phases */
 int bn254_miller_loop_batch(bn254_ctx*, const uint8_t* g1s, const uint8_t* g2s, size_t k, size_t n, uint8_t* f_out384, uint8_t* status);

@@ -921,7 +921,8 @@ static void miller_of_pairs(fq12 *f, const g1 *ps, const g2 *qs, size_t n) {
 static void pairing_batch(fq12 *gt, const g1 *ps, const g2 *qs, size_t n) {
   fq12 f;
   miller_of_pairs(&f, ps, qs, n);
-  if (!fq12_final_exp(gt, &f)) *gt = FQ12_ONE; /* f = 0 is impossible for valid inputs */
+  /* f = 0 is impossible for points of the curve (bn::pairing_batch would panic): fail closed, the result is not one */
+  if (!fq12_final_exp(gt, &f)) *gt = f;
 }
 
 /* ------------------------------------------------------------------ init */

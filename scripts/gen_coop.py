@@ -290,7 +290,7 @@ PLANS = [("MUL", plan_mul), ("SQR", plan_sqr), ("SPARSE_A", lambda: plan_sparse(
          ("INV_C", plan_inv_c)]
 
 # ------------------------------------------------------------------------------------------------ programs
-OPS = ["END", "DOT", "LINE", "LOADP", "LOADS", "STORE", "COPY_PS_CONJ", "CONJP", "FROBP", "INVT", "ONE", "CHECK", "LOADF", "STOREF", "XLANE"]
+OPS = ["END", "DOT", "LINE", "LOADP", "LOADS", "STORE", "COPY_PS_CONJ", "CONJP", "FROBP", "INVT", "ONE", "CHECK", "LOADF", "STOREF", "XLANE", "LOADFS"]
 OPC = {n: i for i, n in enumerate(OPS)}
 PLAN_ID = {n: i for i, (n, _) in enumerate(PLANS)}
 CONJ_FLAG = 0x80
@@ -578,6 +578,13 @@ def gen_tables():
                        ("MILLER1", prog_miller(1) + [ins("STOREF"), ins("END")]),
                        ("MILLER2", prog_miller(2) + [ins("STOREF"), ins("END")]),
                        ("MULTI", prog_multi_miller(MULTI_K) + [ins("STOREF"), ins("END")]),
+                       # the same with fewer pairs per lane: the last, partial wave of a multi-pairing is re-cut into more blocks
+                       ("MULTI4", prog_multi_miller(4) + [ins("STOREF"), ins("END")]),
+                       ("MULTI2", prog_multi_miller(2) + [ins("STOREF"), ins("END")]),
+                       ("MULTI1", prog_multi_miller(1) + [ins("STOREF"), ins("END")]),
+                       # finish of an aggregate check: Miller value of ONE line stream (sum of signatures, -G2) times the value in
+                       # fio (the product of the exchanged partials), final exponentiation, verdict
+                       ("FINISH", prog_miller(1) + [ins("LOADFS"), ins("DOT", PLAN_ID["MUL"])] + prog_final_exp() + [ins("CHECK"), ins("END")]),
                        ("FINALEXP", [ins("LOADF")] + prog_final_exp() + [ins("STOREF"), ins("CHECK"), ins("END")])):
         prog = add_xi_skip(prog0)
         o.append("#define K_COOP_PROG_%s_LEN %d" % (name, len(prog)))

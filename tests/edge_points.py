@@ -34,3 +34,29 @@ def subgroup_edge_points():
     out.append((raw(P.g2_mul(t, h2)), True))
     out.append((raw(P.g2_mul(P.G2_GEN, P.R - 1)), True))
     return out
+
+
+_OUTSIDE = None
+
+
+def twist_point_outside_g2():
+    """128 raw bytes of a point on the twist that is NOT in the r-torsion (a random twist point: the cofactor is ~2^254)."""
+    global _OUTSIDE
+    if _OUTSIDE is None:
+        import random as _r
+        import sys as _s
+        _s.path.insert(0, os.path.join(ROOT, "oracle"))
+        _s.path.insert(0, os.path.join(ROOT, "tests"))
+        import pyoracle as P
+        import oracle_lib as O
+        rng = _r.Random(4242)
+        while True:
+            x = (rng.randrange(P.Q), rng.randrange(P.Q))
+            y2 = P.f2_add(P.f2_mul(P.f2_mul(x, x), x), P.B2)
+            y = P.f2_sqrt(y2)
+            if y is not None and P.f2_mul(y, y) == y2:
+                break
+        raw = b"".join(c.to_bytes(32, "big") for c in (x[0], x[1], y[0], y[1]))
+        assert O.g2_validate_uncompressed(raw) == O.INVALID_GROUP_POINT
+        _OUTSIDE = raw
+    return _OUTSIDE

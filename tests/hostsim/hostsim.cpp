@@ -345,12 +345,14 @@ API int hs_coop_plan(int plan, const uint8_t* p_in, const uint8_t* s_in, uint8_t
   return 0;
 }
 
-// multi-pairing program: n <= 32 * COOP_MULTI_K pairs (g1 64 B, g2 128 B each) -> the block's Miller product (tower order)
-API int hs_coop_multi_miller(const uint8_t* g1s, const uint8_t* g2s, size_t n, uint8_t* f_out) {
+// multi-pairing program `which` (CPROG_MULTI8 / 4 / 2 / 1): n <= 32 * mk pairs (g1 64 B, g2 128 B each) -> the block's Miller
+// product (tower order)
+API int hs_coop_multi_miller_k(int which, const uint8_t* g1s, const uint8_t* g2s, size_t n, uint8_t* f_out) {
+  const int mk = coop_multi_k(which);
   coop_sim S;
   S.lanes = COOP_LANES;
   lines_consts K;
-  for (size_t slot = 0; slot < (size_t)COOP_LANES * COOP_MULTI_K; slot++) {
+  for (size_t slot = 0; slot < (size_t)COOP_LANES * mk; slot++) {
     size_t lane = slot % COOP_LANES;
     int stream = (int)(slot / COOP_LANES);
     bool use = false;
@@ -368,13 +370,35 @@ API int hs_coop_multi_miller(const uint8_t* g1s, const uint8_t* g2s, size_t n, u
       h.x = p.x;
       h.y = p.y;
     }
-    item_pair_lines(S.lines.data(), S.n_pad, lane, stream, use, &h, q.x, q.y, &K);
+    item_pair_lines(S.lines.data(), S.n_pad, lane, stream, mk, use, &h, q.x, q.y, &K);
   }
-  S.run(K_COOP_PROG_MULTI);
+  S.run(coop_program(which));
   fq12 f;
   S.get_fio(&f);
   fq12_to_be(f_out, &f);
   return 0;
+}
+API int hs_coop_multi_miller(const uint8_t* g1s, const uint8_t* g2s, size_t n, uint8_t* f_out) {
+  return hs_coop_multi_miller_k(CPROG_MULTI8, g1s, g2s, n, f_out);
+}
+// finish of an aggregate check (program FINISH, what bn254_finish_distinct_dev runs): f_in = product of the exchanged partials,
+// sig = the G1 point paired with -G2 (all-zero = infinity: that pair is skipped).  Returns the verdict.
+API int hs_coop_finish(const uint8_t* f_in, const uint8_t* sig) {
+  ensure_init();
+  fq12 f;
+  if (!fq12_from_be(&f, f_in)) return ST_NOT_MEMBER;
+  g1j s;
+  int st = g1_from_raw(&s, sig);
+  if (st) return st;
+  coop_sim S;
+  S.set_fio(&f);
+  fq2 sxy;
+  sxy.c0 = s.x;
+  sxy.c1 = s.y;
+  for (int m = 0; m < K_N_LINES; m++)
+    coop_emit_scaled_v(S.lines.data(), m, S.n_pad, 0, !pt_is_inf(&s), g_lines[m].ell_0, g_lines[m].ell_vw, g_lines[m].ell_vv, sxy);
+  S.run(K_COOP_PROG_FINISH);
+  return S.status;
 }
 
 // fixed-base tables (curve.cuh comb_build_row / pt_mul_fixed), built on the host exactly as k_init_comb does on the device

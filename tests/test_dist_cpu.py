@@ -59,6 +59,19 @@ def _worker(rank, world, port, q):
         assert D.aggregate_verify_distinct_sharded(msgs, 32, pks, agg, partial, finish) == 0
         wrong = O.g1_add(agg, sigs[:64])[1]
         assert D.aggregate_verify_distinct_sharded(msgs, 32, pks, wrong, partial, finish) == 9
+        # same-message aggregate over sharded keys (config 4, /root/reference/examples/bn254.rs:25-32): per-rank sums, one
+        # all-gather of the 64 + 128 byte partial sums, the last additions and one verify on every rank
+        msg = b"sample"
+        s_same = b"".join(O.sign(msg, sks[32 * i:32 * i + 32])[1] for i in range(n))
+        lo, hi = D.shard_range(n, rank, world)
+        g1s = lambda pts: O.g1_sum(pts, len(pts) // 64)[::-1]
+        g2s = lambda pts: O.g2_sum(pts, len(pts) // 128)[::-1]
+        vfy1 = lambda m, s, p: O.verify(m, s, p)
+        assert D.aggregate_verify_same_msg_sharded(msg, s_same[64 * lo:64 * hi], pks[128 * lo:128 * hi], g1s, g2s, vfy1) == 0
+        bad_same = s_same[:64 * 5] + s_same[:64] + s_same[64 * 6:]  # item 5 lives on rank 1
+        assert D.aggregate_verify_same_msg_sharded(msg, bad_same[64 * lo:64 * hi], pks[128 * lo:128 * hi], g1s, g2s, vfy1) == 9
+        # the split must not matter: the whole-input sums verify under the oracle as well
+        assert O.verify(msg, O.g1_sum(s_same, n)[1], O.g2_sum(pks, n)[1]) == 0
         assert [D.shard_range(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
         assert [D.shard_range(1, r, 2) for r in range(2)] == [(0, 1), (1, 1)]
         q.put((rank, "ok"))

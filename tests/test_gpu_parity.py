@@ -32,6 +32,9 @@ def E():
     from bn254_b200 import build, engine
     build.build()
     engine.context(0)  # raises without a GPU / the CUDA library: no fallback
+    # The oracle restates the crate's functions over values of its TYPES (infinity is a value, pairing_batch skips it), so the
+    # module's default context runs under the typed input policy; the untrusted (default) policy has its own tests below.
+    engine.set_input_policy(engine.INPUTS_TYPED)
     return engine
 
 
@@ -671,3 +674,299 @@ def test_verify_workspace_chunking(E):
         assert not fast and st == want
     finally:
         small.close()
+
+
+# ---------------------------------------------------------------------------------------------- input policy, hooks, long messages
+def _untrusted_expect(msg, sig, pk):
+    """What a caller of the crate gets from bytes: PublicKey::from_uncompressed, Signature::from_uncompressed, ECDSA::verify."""
+    return O.g2_validate_uncompressed(pk) or O.g1_validate_uncompressed(sig) or O.verify(msg, sig, pk)
+
+
+def test_untrusted_input_policy(E):
+    """Default policy of a fresh context: bytes are decoded like from_uncompressed.  Raw (0, 0) inputs -- a universal
+    forgery under the typed policy, where both pairs would be skipped -- fail with InvalidGroupPoint, and so does a key on the
+    twist but outside G2; statuses equal the oracle's composition of the crate's three calls."""
+    import edge_points
+    from bn254_b200._native import Context
+    ctx = Context(0)
+    try:
+        assert ctx.input_policy == E.INPUTS_UNTRUSTED
+        n = 64
+        msgs, sks, sigs, pks = _signed_set(E, n, seed=301)
+        msgs, sigs, pks = bytearray(msgs), bytearray(sigs), bytearray(pks)
+        sigs[0:64] = bytes(64); pks[0:128] = bytes(128)                    # both "infinity"
+        sigs[64:128] = bytes(64)                                          # signature (0, 0), real key
+        pks[128 * 2:128 * 3] = bytes(128)                                 # key (0, 0), real signature
+        pks[128 * 3:128 * 4] = edge_points.twist_point_outside_g2()       # on the twist, not in the r-torsion
+        sigs[64 * 4 + 63] ^= 1                                            # off-curve signature
+        pks[128 * 5:128 * 5 + 32] = be(Q + 1)                             # coordinate >= q
+        msgs[32 * 6] ^= 1                                                 # plain wrong message
+        msgs, sigs, pks = bytes(msgs), bytes(sigs), bytes(pks)
+        got = E.verify_batch(msgs, 32, sigs, pks, ctx=ctx)
+        want = bytes(_untrusted_expect(msgs[32 * i:32 * i + 32], sigs[64 * i:64 * i + 64], pks[128 * i:128 * i + 128]) for i in range(n))
+        assert got == want
+        assert list(got[:7]) == [O.INVALID_GROUP_POINT] * 5 + [O.NOT_MEMBER, O.VERIFICATION_FAILED] and not any(got[7:])
+        # the same inputs under the typed policy: item 0 is accepted (both pairs skipped) -- the reason the default is untrusted
+        assert E.verify_batch(msgs, 32, sigs, pks)[0] == 0
+        # check_public_keys and the aggregate checks follow the policy too
+        g1 = E.derive_pk_g1_batch(sks)
+        assert E.check_public_keys_batch(bytes(128) + pks[128:256], bytes(64) + g1[64:128], ctx=ctx) == bytes([O.INVALID_GROUP_POINT, 0])
+        assert E.aggregate_verify_same_msg(b"m", bytes(64), bytes(128), ctx=ctx) == O.INVALID_GROUP_POINT
+        assert E.aggregate_verify_same_msg(b"m", bytes(64), bytes(128)) == 0          # typed: infinity sums, both pairs skipped
+        vm, vs, vp = msgs[32 * 7:32 * 40], sigs[64 * 7:64 * 40], pks[128 * 7:128 * 40]
+        agg = E.g1_sum(vs)[0]
+        assert E.aggregate_verify_distinct(vm, 32, vp, agg, ctx=ctx) == 0
+        assert E.aggregate_verify_distinct(vm, 32, vp[:128 * 5] + edge_points.twist_point_outside_g2() + vp[128 * 6:], agg, ctx=ctx) == O.INVALID_GROUP_POINT
+        # randomised batch verification keeps verify_batch's statuses under the same policy
+        st, fast = E.verify_batch_rlc(msgs, 32, sigs, pks, synth.rand_bytes(9, 16 * n), ctx=ctx)
+        assert st == want and not fast
+    finally:
+        ctx.close()
+
+
+def test_hash_to_point_error_hook(E):
+    """/root/reference/src/hash.rs:62: HashToPointError after the last counter.  With the try limit lowered to k (test hook)
+    every message whose accepted counter is >= k must come back with status 1 from hash, sign and verify -- through the
+    per-thread loop (small batch) and through the compacting rounds (large batch)."""
+    from bn254_b200._native import Context
+    ctx = Context(0)
+    try:
+        E.set_input_policy(E.INPUTS_TYPED, ctx=ctx)
+        for n, k in ((300, 1), (300, 3), (6000, 2), (6000, 14)):
+            msgs, sks = synth.messages(n, 32, seed=400 + k), synth.secret_keys(n, seed=500 + k)
+            ctrs = [O.hash_to_g1(msgs[32 * i:32 * i + 32])[2] for i in range(n)]
+            want = bytes(O.HASH_TO_POINT if c >= k else 0 for c in ctrs)
+            assert any(want) and not all(want)
+            E.set_hash_try_limit(255, ctx=ctx)
+            sigs, st = E.sign_batch(msgs, 32, sks, ctx=ctx)
+            pks = E.derive_pk_g2_batch(sks, ctx=ctx)
+            assert not any(st)
+            E.set_hash_try_limit(k, ctx=ctx)
+            pts, st = E.hash_to_g1_batch(msgs, 32, n, ctx=ctx)
+            assert st == want
+            assert all(pts[64 * i:64 * i + 64] == (bytes(64) if want[i] else O.hash_to_g1(msgs[32 * i:32 * i + 32])[1]) for i in range(0, n, 37))
+            s2, st = E.sign_batch(msgs, 32, sks, ctx=ctx)
+            assert st == want and all(s2[64 * i:64 * i + 64] == (bytes(64) if want[i] else sigs[64 * i:64 * i + 64]) for i in range(n))
+            assert E.verify_batch(msgs, 32, sigs, pks, ctx=ctx) == want           # the hash error propagates (src/ecdsa.rs:53)
+            E.set_input_policy(E.INPUTS_UNTRUSTED, ctx=ctx)
+            assert E.verify_batch(msgs, 32, sigs, pks, ctx=ctx) == want
+            E.set_input_policy(E.INPUTS_TYPED, ctx=ctx)
+    finally:
+        ctx.close()
+
+
+@pytest.mark.parametrize("msg_len", [55, 64, 65, 200])
+def test_verify_long_messages(E, msg_len):
+    """Messages that do not share one SHA-256 block with the counter (>= 55 bytes) take the per-thread hash loop inside verify:
+    4096 triples per length, a seeded 3 % invalid, verdicts equal to the oracle's."""
+    n = 4096
+    msgs, sks = synth.messages(n, msg_len, seed=600 + msg_len), synth.secret_keys(n, seed=700 + msg_len)
+    sigs, st = E.sign_batch(msgs, msg_len, sks)
+    assert not any(st)
+    assert sigs[:64 * 64] == O.sign_batch(msgs[:64 * msg_len], msg_len, sks[:64 * 32], 64, NTHREADS)[0]
+    pks = E.derive_pk_g2_batch(sks)
+    m = bytearray(msgs)
+    bad = sorted(random.Random(msg_len).sample(range(n), n // 32))
+    for i in bad:
+        m[msg_len * i + msg_len - 1] ^= 0x80
+    got = E.verify_batch(bytes(m), msg_len, sigs, pks)
+    assert {i for i in range(n) if got[i]} == set(bad) and all(got[i] == O.VERIFICATION_FAILED for i in bad)
+    assert got == O.verify_batch(bytes(m), msg_len, sigs, pks, n, NTHREADS)
+
+
+def test_full_size_sign_2_20(E):
+    """configs[2]: 2^20 distinct messages and keys signed in one call; a seeded sample of 1024 signatures equals the oracle's
+    bit for bit, and every signature verifies (so none is wrong in a way the sample missed)."""
+    n = 1 << 20
+    msgs, sks, sigs, pks = _signed_set(E, n, seed=11)
+    idx = np.sort(np.random.default_rng(12).choice(n, size=1024, replace=False))
+    sm = b"".join(msgs[32 * i:32 * i + 32] for i in idx)
+    sk = b"".join(sks[32 * i:32 * i + 32] for i in idx)
+    want, st = O.sign_batch(sm, 32, sk, len(idx), NTHREADS)
+    assert not any(st) and want == b"".join(sigs[64 * i:64 * i + 64] for i in idx)
+    assert E.verify_batch(msgs, 32, sigs, pks) == bytes(n)
+
+
+def test_full_size_rlc_2_20(E):
+    """Randomised batch verification at 2^20 triples: all valid -> fast path and all-zero statuses; with 100 seeded invalid
+    items -> exactly verify_batch's statuses (themselves checked against the oracle on the invalid items and a sample)."""
+    n = 1 << 20
+    msgs, sks, sigs, pks = _signed_set(E, n, seed=21)
+    coeffs = synth.rand_bytes(22, 16 * n)
+    st, fast = E.verify_batch_rlc(msgs, 32, sigs, pks, coeffs, pks_in_g2=True)
+    assert fast and st == bytes(n)
+    bad = np.sort(np.random.default_rng(23).choice(n, size=100, replace=False))
+    s = np.frombuffer(sigs, dtype=np.uint8).reshape(n, 64).copy()
+    s[bad] = s[(bad + 1) % n]
+    sigs2 = s.tobytes()
+    st, fast = E.verify_batch_rlc(msgs, 32, sigs2, pks, coeffs)
+    want = E.verify_batch(msgs, 32, sigs2, pks)
+    assert not fast and st == want
+    assert {int(i) for i in np.nonzero(np.frombuffer(want, dtype=np.uint8))[0]} == {int(i) for i in bad}
+    idx = np.concatenate([bad, np.arange(0, n, n // 400)])
+    pick = lambda b, w: b"".join(b[w * i:w * i + w] for i in idx)
+    assert O.verify_batch(pick(msgs, 32), 32, pick(sigs2, 64), pick(pks, 128), len(idx), NTHREADS) == bytes(want[i] for i in idx)
+
+
+# ---------------------------------------------------------------------------------------------- aggregate checks on the device
+def _dev(b):
+    import torch
+    return torch.frombuffer(bytearray(b), dtype=torch.uint8).cuda()
+
+
+def test_distinct_aggregate_device_path_vs_oracle(E):
+    """bn254_distinct_payload_dev + bn254_finish_distinct_dev (what the multi-GPU step runs, here with the records of several
+    slices on one GPU): verdicts equal the oracle's fold over the same pairs -- accept, a forged signature, a key that is not on
+    the curve (first failing item's status), a slice holding infinity keys -- and the cooperative finish agrees with the
+    one-thread finish (pairing mode 1)."""
+    import torch
+    from bn254_b200 import dist as D
+    from bn254_b200._native import I, S
+    ctx = E.context(0)
+    n = 2500
+    msgs, sks, sigs, pks = _signed_set(E, n, seed=801)
+    neg_g2 = O.g2_neg(O.derive_pk_g2(be(1))[1])[1]
+    hs = E.hash_to_g1_batch(msgs, 32, n)[0]
+
+    def oracle_fold(pk_bytes, agg):
+        for i in range(n):
+            stp = O.miller_product(hs[64 * i:64 * i + 64], pk_bytes[128 * i:128 * i + 128], 1)[0]   # decode status of pair i
+            if stp:
+                return stp
+        return O.pairing_check(hs + agg, pk_bytes + neg_g2, n + 1)[0]
+
+    def run(pk_bytes, sig_bytes, cuts, local_sigs, mode=0):
+        ctx.call("bn254_set_pairing_mode", I(mode))
+        try:
+            recs = torch.zeros(448 * (len(cuts) - 1), dtype=torch.uint8, device="cuda")
+            d_m, d_p, d_s = _dev(msgs), _dev(pk_bytes), _dev(sig_bytes)
+            for r, (a, b) in enumerate(zip(cuts, cuts[1:])):
+                ctx.call("bn254_distinct_payload_dev", d_m[32 * a:], S(32), d_p[128 * a:], d_s[64 * a:] if local_sigs else None, S(b - a),
+                         recs[448 * r:448 * r + 448])
+            verdict = torch.zeros(1, dtype=torch.uint8, device="cuda")
+            agg = None if local_sigs else _dev(E.g1_sum(sig_bytes)[0])
+            ctx.call("bn254_finish_distinct_dev", recs, S(len(cuts) - 1), agg, verdict)
+            ctx.sync()
+            return int(verdict.cpu()[0])
+        finally:
+            ctx.call("bn254_set_pairing_mode", I(0))
+
+    cuts = [0, 700, 701, 1900, n]
+    agg = E.g1_sum(sigs)[0]
+    assert oracle_fold(pks, agg) == 0
+    for local in (True, False):
+        for mode in (0, 1):
+            assert run(pks, sigs, cuts, local, mode) == 0
+    forged = sigs[:64 * 1234] + sigs[64 * 1235:64 * 1236] + sigs[64 * 1235:]       # item 1234 carries item 1235's signature
+    assert oracle_fold(pks, E.g1_sum(forged)[0]) == O.VERIFICATION_FAILED
+    for local in (True, False):
+        assert run(pks, forged, cuts, local) == O.VERIFICATION_FAILED
+    assert run(pks, forged, cuts, True, 1) == O.VERIFICATION_FAILED
+    badkey = bytearray(pks)
+    badkey[128 * 2000 + 127] ^= 1                                                 # third slice: not on the curve
+    badkey[128 * 2300:128 * 2301] = be(Q) + bytes(96)                             # fourth slice: a later, different error
+    assert oracle_fold(bytes(badkey), agg) == O.INVALID_GROUP_POINT
+    assert run(bytes(badkey), sigs, cuts, True) == O.INVALID_GROUP_POINT
+    assert run(bytes(badkey), sigs, cuts, False, 1) == O.INVALID_GROUP_POINT
+    # the class bench.py drives, world = 1
+    agg_dev = D.DistinctAggregate(ctx, world=1)
+    agg_dev.step(_dev(msgs), 32, _dev(pks), _dev(sigs), n)
+    assert agg_dev.status() == 0
+    agg_dev.step(_dev(msgs), 32, _dev(pks), _dev(forged), n)
+    assert agg_dev.status() == O.VERIFICATION_FAILED
+
+
+def test_distinct_aggregate_2_20_pairs(E):
+    """configs[4] at 2^20 pairs on one GPU through the device path: several launches of whole waves plus the re-cut last wave.
+    Accept for the honest aggregate; one forged signature, one key off the curve and one key outside G2 (untrusted policy) are
+    each reported -- the verdicts the oracle's fold gives by construction (its full fold is checked at 2 500 pairs above)."""
+    import edge_points
+    from bn254_b200 import dist as D
+    from bn254_b200._native import Context
+    n = 1 << 20
+    msgs, sks, sigs, pks = _signed_set(E, n, seed=811)
+    ctx = E.context(0)
+    agg = D.DistinctAggregate(ctx, world=1)
+    d_m, d_p, d_s = _dev(msgs), _dev(pks), _dev(sigs)
+    agg.step(d_m, 32, d_p, d_s, n)
+    assert agg.status() == 0
+    agg.step(d_m, 32, d_p, d_s[64:], n - 1)                # pairs 0 .. n-2 against signatures 1 .. n-1: rejected
+    assert agg.status() == O.VERIFICATION_FAILED
+    forged = bytearray(sigs)
+    forged[64 * 777777:64 * 777778] = sigs[64 * 5:64 * 6]
+    agg.step(d_m, 32, d_p, _dev(bytes(forged)), n)
+    assert agg.status() == O.VERIFICATION_FAILED
+    bad = bytearray(pks)
+    bad[128 * 999999 + 64] ^= 2
+    agg.step(d_m, 32, _dev(bytes(bad)), d_s, n)
+    assert agg.status() == O.INVALID_GROUP_POINT
+    strict = Context(0)
+    try:
+        out = bytearray(pks)
+        out[128 * 424242:128 * 424243] = edge_points.twist_point_outside_g2()
+        a2 = D.DistinctAggregate(strict, world=1)
+        a2.step(d_m, 32, _dev(bytes(out)), d_s, n)
+        assert a2.status() == O.INVALID_GROUP_POINT
+    finally:
+        strict.close()
+
+
+def test_same_message_aggregate_device_path(E):
+    from bn254_b200 import dist as D
+    ctx = E.context(0)
+    n = 5000
+    msg = b"one message, many signers"
+    sks = synth.secret_keys(n, seed=821)
+    sigs, st = E.sign_batch(msg * n, len(msg), sks)
+    pks = E.derive_pk_g2_batch(sks)
+    agg = D.SameMessageAggregate(ctx, world=1)
+    agg.step(_dev(msg), len(msg), _dev(sigs), _dev(pks), n)
+    assert agg.status() == 0 and O.verify(msg, E.g1_sum(sigs)[0], E.g2_sum(pks)[0]) == 0
+    agg.step(_dev(msg), len(msg), _dev(sigs[64:]), _dev(pks), n - 1)
+    assert agg.status() == O.VERIFICATION_FAILED
+
+
+def test_two_rank_nccl_aggregates():
+    """world_size 2 over NCCL on two GPUs of the box (skipped on a one-GPU box): tests/dist_gpu_worker.py drives the device
+    paths of bn254_b200/dist.py with the CUDA engine -- a forged signature and an undecodable key on rank 1 included."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", "29533",
+           os.path.join(ROOT, "tests", "dist_gpu_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "DIST_GPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_format_pairing_check_c_abi(E):
+    """bn254_format_pairing_check_batch (/root/reference/src/utils.rs:197-239) in batch form: both input forms agree, the layout
+    is the little-endian image of the oracle's points, the formatted pairs pass the pairing check, and errors come in the
+    reference's order (hash, public key, signature)."""
+    n = 200
+    msgs, sks, sigs, pks = _signed_set(E, n, seed=831)
+    cs, st1 = E.g1_compress_batch(sigs)
+    cp, st2 = E.g2_compress_batch(pks)
+    assert not any(st1) and not any(st2)
+    a, sta = E.format_pairing_check_batch(msgs, 32, cs, cp, True)
+    b, stb = E.format_pairing_check_batch(msgs, 32, sigs, pks, False)
+    assert a == b and not any(sta) and not any(stb)
+    rev = lambda x: b"".join(x[i:i + 32][::-1] for i in range(0, len(x), 32))
+    neg_g2 = O.g2_neg(O.derive_pk_g2(be(1))[1])[1]
+    for i in range(0, n, 17):
+        blob = rev(a[384 * i:384 * i + 384])
+        assert blob == O.hash_to_g1(msgs[32 * i:32 * i + 32])[1] + pks[128 * i:128 * i + 128] + sigs[64 * i:64 * i + 64] + neg_g2
+    g1s = b"".join(rev(a[384 * i:384 * i + 64]) + rev(a[384 * i + 192:384 * i + 256]) for i in range(n))
+    g2s = b"".join(rev(a[384 * i + 64:384 * i + 192]) + rev(a[384 * i + 256:384 * i + 384]) for i in range(n))
+    assert E.pairing_check_batch(g1s, g2s, 2, n) == bytes(n)
+    bad_pk = bytes([0x0c]) + cp[1:65]            # bad sign byte -> InvalidEncoding
+    bad_sig = bytes([0x04]) + cs[1:33]
+    _, st = E.format_pairing_check_batch(msgs[:64], 32, bad_sig + cs[33:66], bad_pk + cp[65:130], True)
+    assert st == bytes([O.INVALID_ENCODING, 0])
+    _, st = E.format_pairing_check_batch(msgs[:32], 32, bad_sig, cp[:65], True)
+    assert st == bytes([O.INVALID_ENCODING])
+    from bn254_b200 import Error, format_pairing_check_uncompressed_values
+    with pytest.raises(Error) as e:
+        format_pairing_check_uncompressed_values(b"m", sigs[:64] + b"x", pks[:128])
+    assert e.value.variant == "SerializationError"

@@ -298,6 +298,44 @@ def test_coop_multi_pairing_program(hs):
     assert f.raw == O.miller_product(g1s, g2s, n)[1]
 
 
+def test_coop_multi_pairing_programs_all_k(hs):
+    """The shorter multi-pairing programs (4, 2, 1 pairs per lane: the re-cut last wave of a big multi-pairing) give the
+    oracle's Miller product too."""
+    rng = random.Random(18)
+    for which, mk in ((6, 4), (7, 2), (8, 1)):
+        n = 32 * mk - 5
+        g1s = b"".join(O.derive_pk_g1(be(rng.randrange(1, R)))[1] for _ in range(n))
+        g2s = b"".join(O.derive_pk_g2(be(rng.randrange(1, R)))[1] for _ in range(n))
+        f = buf(384)
+        assert hs.hs_coop_multi_miller_k(which, g1s, g2s, n, f) == 0
+        assert f.raw == O.miller_product(g1s, g2s, n)[1], mk
+
+
+def test_coop_finish_program(hs):
+    """Program FINISH (bn254_finish_distinct_dev): Miller value of (sig, -G2) times the exchanged product, final
+    exponentiation, verdict -- against the oracle's verdict for the same aggregate, accept and reject."""
+    rng = random.Random(19)
+    n = 3
+    msgs = [bytes([i]) * 32 for i in range(n)]
+    sks = [be(rng.randrange(1, R)) for _ in range(n)]
+    hs_pts = b"".join(O.hash_to_g1(m)[1] for m in msgs)
+    pks = b"".join(O.derive_pk_g2(k)[1] for k in sks)
+    sigs = [O.sign(m, k)[1] for m, k in zip(msgs, sks)]
+    agg = bytes(64)
+    for s in sigs:
+        agg = O.g1_add(agg, s)[1]
+    part = O.miller_product(hs_pts, pks, n)[1]
+    assert hs.hs_coop_finish(part, agg) == 0
+    assert hs.hs_coop_finish(part, O.g1_add(agg, sigs[0])[1]) == O.VERIFICATION_FAILED
+    assert hs.hs_coop_finish(part, bytes(64)) == O.VERIFICATION_FAILED        # signature pair skipped: product != 1
+    one = be(1) + bytes(352)
+    assert hs.hs_coop_finish(one, bytes(64)) == 0                             # empty product
+    # the rank-local form: the (sum sig, -G2) pair already inside the partial, nothing to add at the finish
+    neg_g2 = O.g2_neg(O.derive_pk_g2(be(1))[1])[1]
+    full = O.miller_product(hs_pts + agg, pks + neg_g2, n + 1)[1]
+    assert hs.hs_coop_finish(full, bytes(64)) == 0
+
+
 def test_fixed_base_tables(hs):
     """G * sk through the 64 x 15 fixed-base tables == the ladder == the oracle, incl. the reference's key KATs, keys > r
     (reduced mod r like Fr::from_slice), 0, 1, r - 1 and scalars with zero nibbles."""
