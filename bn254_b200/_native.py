@@ -13,7 +13,7 @@ SYMBOLS = [
     "bn254_hash_to_g1_batch", "bn254_hash_to_g1_batch_dev", "bn254_hash_to_g1_var",
     "bn254_sign_batch", "bn254_sign_batch_dev", "bn254_verify_batch", "bn254_verify_batch_dev",
     "bn254_verify_batch_rlc", "bn254_verify_batch_rlc_dev",
-    "bn254_check_public_keys_batch", "bn254_pairing_check_batch",
+    "bn254_check_public_keys_batch", "bn254_pairing_check_batch", "bn254_pairing_check_batch_dev",
     "bn254_g1_sum", "bn254_g2_sum", "bn254_g1_sum_dev", "bn254_g2_sum_dev",
     "bn254_derive_pk_g2_batch", "bn254_derive_pk_g1_batch", "bn254_g1_mul_batch", "bn254_g2_mul_batch",
     "bn254_g1_compress_batch", "bn254_g1_decompress_batch", "bn254_g2_compress_batch", "bn254_g2_decompress_batch",

@@ -598,6 +598,45 @@ __global__ void __launch_bounds__(BN_BLOCK, BN_LINES_MINB) k_pair_lines(const g1
   }
   item_pair_lines(lines, L, p % L, (int)(p / L), mk, use, &h, q.x, q.y, &consts[threadIdx.x]);
 }
+// ---- bn::pairing_batch(k pairs) == one through the cooperative machine (k = 1, 2): decode statuses first (first failing
+// pair in order, G1 before G2, as a left-to-right decode would report), then one thread per (item, pair) writes the pair's
+// line stream, then the machine runs Miller loop + final exponentiation + verdict per item
+__global__ void __launch_bounds__(BN_BLOCK) k_pairs_decode(const uint8_t* __restrict__ g1s, const uint8_t* __restrict__ g2s, size_t k, size_t n,
+                                                           uint8_t* __restrict__ status) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int st = ST_OK;
+  for (size_t j = 0; j < k && !st; j++) {
+    g1j p;
+    g2j q;
+    st = g1_from_raw(&p, g1s + 64 * (k * i + j));
+    if (!st) st = g2_from_raw(&q, g2s + 128 * (k * i + j));
+  }
+  status[i] = (uint8_t)st;
+}
+__global__ void __launch_bounds__(BN_BLOCK, BN_LINES_MINB) k_item_pair_lines(const uint8_t* __restrict__ g1s, const uint8_t* __restrict__ g2s, int k,
+                                                                             size_t n, size_t n_pad, u4* __restrict__ lines,
+                                                                             const uint8_t* __restrict__ status) {
+  __shared__ lines_consts consts[BN_BLOCK];
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * (size_t)k) return;
+  const size_t i = t / k;
+  const int s = (int)(t % k);
+  if (status[i]) return;
+  g1j p;
+  g2j q;
+  g1_from_raw(&p, g1s + 64 * t);
+  g2_from_raw(&q, g2s + 128 * t);
+  const bool use = !pt_is_inf(&p) && !pt_is_inf(&q);
+  g1aff h;
+  h.x = p.x;
+  h.y = p.y;
+  if (!use) {
+    q.x = fq2_one();
+    q.y = fq2_one();
+  }
+  item_pair_lines(lines, n_pad, i, s, k, use, &h, q.x, q.y, &consts[threadIdx.x]);
+}
 // lane 0 of every block holds the block's product (power-basis layout fio) -> tower-order Fq12 array
 __global__ void k_coop_gather(const u4* __restrict__ fio, size_t L, size_t blocks, fq12* __restrict__ out) {
   size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1494,6 +1533,31 @@ int bn254_check_public_keys_batch(bn254_ctx* ctx, const uint8_t* pk_g2, const ui
   return 0;
 }
 
+int bn254_pairing_check_batch_dev(bn254_ctx* ctx, const uint8_t* g1s, const uint8_t* g2s, size_t k, size_t n, uint8_t* status) {
+  ENTER();
+  if (n == 0) return 0;
+  ARGCHECK(status && (k == 0 || (g1s && g2s)));
+  if (ctx->pairing_mode == 1 || ctx->pairing_mode >= 3 || (k != 1 && k != 2)) {  // one thread per item: any k
+    DALLOC(F, sizeof(fq12) * n);
+    LAUNCH(k_miller_pairs, grid_for(n), BN_BLOCK, g1s, g2s, k, n, F.as<fq12>(), status);
+    LAUNCH(k_final_exp_check, grid_for(n), BN_BLOCK, F.as<fq12>(), n, status);
+    return 0;
+  }
+  // cooperative machine: k line streams per item (25 KB each), chunked like verify
+  size_t CHUNK = (size_t)1 << ctx->chunk_log2;
+  const size_t cap = n < CHUNK ? n : CHUNK, cap_pad = (cap + COOP_LANES - 1) / COOP_LANES * COOP_LANES;
+  DALLOC(LN, sizeof(u4) * k * COOP_LINE_FQ * 2 * K_N_LINES * cap_pad);
+  DALLOC(GS, sizeof(u4) * COOP_GSLOTS * 6 * 2 * 2 * cap_pad);
+  LAUNCH(k_pairs_decode, grid_for(n), BN_BLOCK, g1s, g2s, k, n, status);
+  for (size_t off = 0; off < n; off += CHUNK) {
+    const size_t m = n - off < CHUNK ? n - off : CHUNK, m_pad = (m + COOP_LANES - 1) / COOP_LANES * COOP_LANES;
+    LAUNCH(k_item_pair_lines, grid_for(m * k), BN_BLOCK, g1s + 64 * k * off, g2s + 128 * k * off, (int)k, m, m_pad, LN.as<u4>(), status + off);
+    int rc = launch_coop_groups(ctx, k == 1 ? CPROG_PAIRING1 : CPROG_VERIFY, m, m_pad, LN.as<u4>(), GS.as<u4>(), (u4*)nullptr, status + off,
+                                m_pad / COOP_LANES);
+    if (rc) return rc;
+  }
+  return 0;
+}
 int bn254_pairing_check_batch(bn254_ctx* ctx, const uint8_t* g1s, const uint8_t* g2s, size_t k, size_t n, uint8_t* status) {
   ENTER();
   if (n == 0) return 0;
@@ -1501,13 +1565,12 @@ int bn254_pairing_check_batch(bn254_ctx* ctx, const uint8_t* g1s, const uint8_t*
   DALLOC(d_g1, 64 * k * n);
   DALLOC(d_g2, 128 * k * n);
   DALLOC(d_st, n);
-  DALLOC(F, sizeof(fq12) * n);
   if (k) {
     H2D(d_g1.p, g1s, 64 * k * n);
     H2D(d_g2.p, g2s, 128 * k * n);
   }
-  LAUNCH(k_miller_pairs, grid_for(n), BN_BLOCK, d_g1.as<uint8_t>(), d_g2.as<uint8_t>(), k, n, F.as<fq12>(), d_st.as<uint8_t>());
-  LAUNCH(k_final_exp_check, grid_for(n), BN_BLOCK, F.as<fq12>(), n, d_st.as<uint8_t>());
+  int rc = bn254_pairing_check_batch_dev(ctx, d_g1.as<uint8_t>(), d_g2.as<uint8_t>(), k, n, d_st.as<uint8_t>());
+  if (rc) return rc;
   D2H(status, d_st.p, n);
   CK(cudaStreamSynchronize(ctx->stream));
   return 0;

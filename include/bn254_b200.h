@@ -138,6 +138,7 @@ int bn254_check_public_keys_batch(bn254_ctx*, const uint8_t* pk_g2, const uint8_
 
 /* bn::pairing_batch(...) == Gt::one() for n independent products of k pairs each (pairs with an infinity are skipped) */
 int bn254_pairing_check_batch(bn254_ctx*, const uint8_t* g1s, const uint8_t* g2s, size_t k, size_t n, uint8_t* status);
+int bn254_pairing_check_batch_dev(bn254_ctx*, const uint8_t* g1s, const uint8_t* g2s, size_t k, size_t n, uint8_t* status);
 
 /* Add / Sub / Neg folds (/root/reference/src/types.rs:126-148,196-218,264-286): out = sum of n points
  * (optionally sum of (-1)^neg[i] * P_i when neg != NULL).  *status = first decode error or 0; an infinite sum is all-zero. */

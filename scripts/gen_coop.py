@@ -576,6 +576,8 @@ def gen_tables():
         o.append("};")
     for name, prog0 in (("VERIFY", prog_miller(2) + prog_final_exp() + [ins("CHECK"), ins("END")]),
                        ("MILLER1", prog_miller(1) + [ins("STOREF"), ins("END")]),
+                       # one full pairing check per item: Miller loop of ONE line stream, final exponentiation, verdict
+                       ("PAIRING1", prog_miller(1) + prog_final_exp() + [ins("CHECK"), ins("END")]),
                        ("MILLER2", prog_miller(2) + [ins("STOREF"), ins("END")]),
                        ("MULTI", prog_multi_miller(MULTI_K) + [ins("STOREF"), ins("END")]),
                        # the same with fewer pairs per lane: the last, partial wave of a multi-pairing is re-cut into more blocks

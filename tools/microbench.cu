@@ -97,7 +97,9 @@ int main() {
   int sms = prop.multiProcessorCount;
   uint32_t* out; long long* cyc;
   cudaMalloc(&out, (size_t)sms * 16 * 256 * 4); cudaMalloc(&cyc, 8);
-  const char* names[6] = {"imad_lo", "imad_hi", "imad_wide", "iadd", "wide_plus_add", "wide_x_carry"};
+  // ("imad_wide": ptxas hoists the loop-invariant product of this pattern and emits IADD3 pairs, so the figure is an add rate;
+  //  "wide_x_carry" is the one that issues one IMAD.WIDE.U32 per iteration -- SASS checked, see profiles/r02_tuning_log.md)
+  const char* names[6] = {"imad_lo", "imad_hi", "imad_wide_hoisted_adds", "iadd", "wide_plus_add", "imad_wide_acc64"};
   double per[6];
   printf("{\"sms\": %d, \"clock_khz_max\": %d", sms, prop.clockRate);
   for (int mode = 0; mode < 6; mode++) {
@@ -110,10 +112,12 @@ int main() {
     if (mode == 0) go(k_rate<0>); else if (mode == 1) go(k_rate<1>); else if (mode == 2) go(k_rate<2>);
     else if (mode == 3) go(k_rate<3>); else if (mode == 4) go(k_rate<4>); else go(k_rate<5>);
     double ops = (double)blocks * 256 * ITERS * NACC * (mode == 4 ? 2 : 1);
-    // whole-grid rate from wall time; clock from block 0's cycle counter (all blocks resident: 8 blocks/SM)
-    double mhz = cycles / (ms * 1e-3) / 1e6;
-    per[mode] = ops / ((double)cycles * sms);
-    printf(", \"%s\": {\"ops_per_clk_per_sm\": %.2f, \"gops\": %.1f, \"sm_mhz\": %.0f}", names[mode], per[mode], ops / (ms * 1e-3) / 1e9, mhz);
+    // whole-grid rate from the CUDA-event time; per-clock figures use the device's maximum SM clock (prop.clockRate), which is
+    // what an unthrottled integer kernel runs at (bench.py samples the real clock next to this).  Block 0's clock64() span is
+    // printed as a cross-check only: round 1 divided it by the whole-grid time and reported a meaningless 245 "MHz".
+    per[mode] = ops / (ms * 1e-3 * (double)prop.clockRate * 1e3 * sms);
+    (void)cycles;
+    printf(", \"%s\": {\"ops_per_clk_per_sm\": %.2f, \"gops\": %.1f}", names[mode], per[mode], ops / (ms * 1e-3) / 1e9);
   }
   // Fq product throughput at several occupancies / ILP
   for (int cfg = 0; cfg < 4; cfg++) {
