@@ -94,23 +94,45 @@ __global__ void __launch_bounds__(BN_BLOCK) k_hash_round(const uint8_t* __restri
     }
   }
 }
-// the few items that survive the compacting rounds finish with the per-thread loop (counters ctr0 .. 254)
-__global__ void __launch_bounds__(BN_BLOCK) k_hash_tail(const uint8_t* __restrict__ msgs, uint32_t msg_len, uint32_t ctr0, uint32_t max_tries,
-                                                        const uint32_t* __restrict__ list_in, const uint32_t* __restrict__ count_in,
-                                                        g1aff* __restrict__ H, uint8_t* __restrict__ status) {
-  const uint32_t total = *count_in;
-  const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
-    const uint32_t i = list_in[t];
-    g1aff h;
-    bool ok = false;
-    for (uint32_t ctr = ctr0; ctr < max_tries && !ok; ctr++) ok = hash_try_1blk(&h.x, &h.y, msgs + (size_t)i * msg_len, msg_len, ctr);
-    if (!ok) {
-      h.x = fq_zero();
-      h.y = fq_zero();
+// ---- counter-parallel hash: one WARP per message, lane l tries counter base + l, the lowest accepted counter wins (exactly the
+// point the sequential loop returns).  32 x the work of the loop per step, but one step (0.2 ms) almost always decides: used for
+// small batches, where the loop's latency is the slowest lane's try count, and for the survivors of the compacting rounds.
+// list_in == NULL: items 0 .. n-1; else items list_in[0 .. *count_in).
+__global__ void __launch_bounds__(BN_BLOCK) k_hash_wide(const uint8_t* __restrict__ msgs, size_t msg_len, const uint64_t* __restrict__ offsets,
+                                                        size_t n, const uint32_t* __restrict__ list_in, const uint32_t* __restrict__ count_in,
+                                                        int ctr0, int max_tries, g1aff* __restrict__ H, uint8_t* __restrict__ status,
+                                                        uint8_t* __restrict__ tries) {
+  const size_t total = list_in ? (size_t)*count_in : n;
+  const unsigned lane = threadIdx.x & 31;
+  const size_t warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  for (size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total; w += warps) {
+    const size_t i = list_in ? list_in[w] : w;
+    const uint8_t* m = offsets ? msgs + offsets[i] : msgs + i * msg_len;
+    const uint64_t len = offsets ? offsets[i + 1] - offsets[i] : msg_len;
+    bool done = false;
+    for (int base = ctr0; base < max_tries && !done; base += 32) {
+      const int ctr = base + (int)lane;
+      g1aff h;
+      bool ok = false;
+      if (ctr < max_tries) ok = hash_to_g1(&h.x, &h.y, m, len, nullptr, ctr + 1, ctr) == ST_OK;
+      const unsigned hit = __ballot_sync(0xffffffffu, ok);
+      if (hit) {
+        if (lane == (unsigned)(__ffs(hit) - 1)) {
+          H[i] = h;
+          status[i] = ST_OK;
+          if (tries) tries[i] = (uint8_t)ctr;
+        }
+        done = true;
+      }
     }
-    H[i] = h;
-    status[i] = ok ? ST_OK : ST_HASH_TO_POINT;
+    if (!done && lane == 0) {
+      g1aff z;
+      z.x = fq_zero();
+      z.y = fq_zero();
+      H[i] = z;
+      status[i] = ST_HASH_TO_POINT;
+      if (tries) tries[i] = 0;
+    }
   }
 }
 
@@ -366,6 +388,9 @@ __global__ void __launch_bounds__(COOP_THREADS, BN_COOP_MINB) k_coop_run(int whi
     while (clock64() - t0 < (long long)slot * stagger) {
     }
   }
+  uint32_t* kq = (uint32_t*)(coop_sm + COOP_SLOTS * 2 * COOP_LANES);  // the k q table of fq_mul9_add, after the group's slots
+  if (threadIdx.x < 88) kq[threadIdx.x] = (&K_KQ_TABLE[0][0])[threadIdx.x];
+  __syncthreads();
   coop_ctx c;
   c.k = threadIdx.x >> 5;
   c.lane = threadIdx.x & 31;
@@ -373,7 +398,7 @@ __global__ void __launch_bounds__(COOP_THREADS, BN_COOP_MINB) k_coop_run(int whi
   c.row = COOP_LANES;
   c.wmode = false;
   c.plans = K_COOP_PLANS;
-  c.kq = nullptr;
+  c.kq = kq;
   c.item = (size_t)blockIdx.x * COOP_LANES + c.lane;
   c.active = c.item < n;
   c.n_pad = n_pad;
@@ -399,6 +424,7 @@ __global__ void __launch_bounds__(COOP_THREADS, BN_COOP_MINB) k_coop_run(int whi
 // sub-partition: they share one multiplier pipe fairly, reach the group barrier together, and never wait for a sibling that
 // is queued behind other groups' warps on a busier sub-partition (in k_coop_run a block's warps are spread over all four
 // sub-partitions and 36 % of the warp-time is spent at the block barrier).  Barriers are per group (named barrier g + 1).
+#define COOP1_SMEM_BYTES (COOP_SMEM_BYTES + 11 * 32) /* + the k q table of fq_mul9_add */
 #define COOP4_GROUPS 4
 #define COOP4_THREADS (COOP4_GROUPS * COOP_THREADS)
 #define COOP4_SMEM_BYTES (COOP4_GROUPS * COOP_SMEM_BYTES + 11 * 32) /* + the k q table of fq_mul9_add */
@@ -1155,7 +1181,7 @@ int bn254_ctx_create(int device, bn254_ctx** out) {
   ctx->launches++;
   if ((e = cudaGetLastError()) != cudaSuccess) return fail("k_init_comb launch", e);
   if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return fail("k_init_lines / k_init_comb", e);
-  if ((e = cudaFuncSetAttribute(k_coop_run, cudaFuncAttributeMaxDynamicSharedMemorySize, COOP_SMEM_BYTES)) != cudaSuccess)
+  if ((e = cudaFuncSetAttribute(k_coop_run, cudaFuncAttributeMaxDynamicSharedMemorySize, COOP1_SMEM_BYTES)) != cudaSuccess)
     return fail("cudaFuncSetAttribute(k_coop_run)", e);
   if ((e = cudaFuncSetAttribute(k_coopw_run, cudaFuncAttributeMaxDynamicSharedMemorySize, COOPW_SMEM_BYTES)) != cudaSuccess)
     return fail("cudaFuncSetAttribute(k_coopw_run)", e);
@@ -1238,24 +1264,32 @@ uint64_t bn254_launch_count(bn254_ctx* ctx) { return ctx ? ctx->launches : 0; }
   CK(name.alloc(bytes))
 
 // ---- device-pointer pipelines (asynchronous on ctx->stream)
-#define BN_HASH_ROUNDS 12
+#define BN_HASH_ROUNDS 6
+#define BN_HASH_WIDE_MAX 8192
 static int hash_dev(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, const uint64_t* offsets, size_t n, g1aff* H, uint8_t* status,
                     uint8_t* tries) {
   if (n == 0) return 0;
-  // small batches, ragged messages, multi-block messages and callers that want the counters: one thread loops per item
   const int cap = ctx->hash_try_limit;
-  if (offsets || tries || msg_len > 54 || n < 4096 || n > 0xffffffffu) {
+  // small batches: one warp per message, 32 counters at a time (latency of ONE try instead of the unluckiest lane's count)
+  if (n <= BN_HASH_WIDE_MAX) {
+    LAUNCH(k_hash_wide, grid_for(n * 32), BN_BLOCK, msgs, msg_len, offsets, n, (const uint32_t*)nullptr, (const uint32_t*)nullptr, 0, cap, H, status,
+           tries);
+    return 0;
+  }
+  // big batches of ragged / multi-block messages, and callers that want the counters: one thread loops per item
+  if (offsets || tries || msg_len > 54 || n > 0xffffffffu) {
     LAUNCH(k_hash_to_g1, grid_for(n), BN_BLOCK, msgs, msg_len, offsets, n, H, status, tries, cap);
     return 0;
   }
-  // compacting rounds: expected survivors of round r = n * 0.527^r; grids are sized with a margin and stride over the list
+  // compacting rounds: expected survivors of round r = n * 0.527^r; grids are sized with a margin and stride over the list.
+  // After BN_HASH_ROUNDS rounds 2 % of the items are left: they finish counter-parallel (one warp each) in one more step.
   DALLOC(lists, sizeof(uint32_t) * 2 * n);
   DALLOC(counts, sizeof(uint32_t) * (BN_HASH_ROUNDS + 1));
   CK(cudaMemsetAsync(counts.p, 0, sizeof(uint32_t) * (BN_HASH_ROUNDS + 1), ctx->stream));
   uint32_t* L[2] = {lists.as<uint32_t>(), lists.as<uint32_t>() + n};
   uint32_t* C = counts.as<uint32_t>();
   double expect = (double)n;
-  const int rounds = cap < BN_HASH_ROUNDS ? cap : BN_HASH_ROUNDS;  // (the tail below marks whatever is left after `cap` tries)
+  const int rounds = cap < BN_HASH_ROUNDS ? cap : BN_HASH_ROUNDS;  // (the last step marks whatever is left after `cap` tries)
   for (int r = 0; r < rounds; r++) {
     size_t threads = r == 0 ? n : (size_t)(expect * 1.25) + 4096;
     if (threads > n) threads = n;
@@ -1263,9 +1297,10 @@ static int hash_dev(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, const u
            r == 0 ? (const uint32_t*)nullptr : C + r, L[r & 1], C + r + 1, H, status);
     expect *= 0.5275;
   }
-  size_t threads = (size_t)(expect * 1.25) + 4096;
-  if (threads > n) threads = n;
-  LAUNCH(k_hash_tail, grid_for(threads), BN_BLOCK, msgs, (uint32_t)msg_len, (uint32_t)rounds, (uint32_t)cap, L[(rounds - 1) & 1], C + rounds, H, status);
+  size_t warps = (size_t)(expect * 1.25) + 4096;
+  if (warps > n) warps = n;
+  LAUNCH(k_hash_wide, grid_for(warps * 32), BN_BLOCK, msgs, msg_len, (const uint64_t*)nullptr, n, L[(rounds - 1) & 1], C + rounds, rounds, cap, H, status,
+         (uint8_t*)nullptr);
   return 0;
 }
 
@@ -1351,8 +1386,12 @@ int bn254_sign_batch(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, const 
 // sub-partition, k_coop4_run) unless the context asks for the one-group-per-block kernel (pairing mode 2)
 static int launch_coop_groups(bn254_ctx* ctx, int which, size_t n, size_t n_pad, const u4* lines, u4* gslots, u4* fio, uint8_t* status,
                               size_t groups) {
-  if (ctx->pairing_mode == 2 || !ctx->coop_groups4)
-    k_coop_run<<<(unsigned)groups, COOP_THREADS, COOP_SMEM_BYTES, ctx->stream>>>(which, n, n_pad, lines, gslots, fio, status, ctx->coop_stagger,
+  // Fewer groups than one full wave of four-group blocks: one group per six-warp block instead, so that the groups spread over
+  // all SMs and a group's warps over the four sub-partitions of its SM -- the latency of a one-item verify drops from 7.6 ms to
+  // about 3 ms in the machine.  (At full load the four-group block is 5 % faster: profiles/r01_tuning_log.md.)
+  const bool small = groups < (size_t)ctx->sm_count * COOP4_GROUPS;
+  if (ctx->pairing_mode == 2 || !ctx->coop_groups4 || small)
+    k_coop_run<<<(unsigned)groups, COOP_THREADS, COOP1_SMEM_BYTES, ctx->stream>>>(which, n, n_pad, lines, gslots, fio, status, ctx->coop_stagger,
                                                                                 (unsigned)ctx->sm_count);
   else
     k_coop4_run<<<(unsigned)((groups + COOP4_GROUPS - 1) / COOP4_GROUPS), COOP4_THREADS, COOP4_SMEM_BYTES, ctx->stream>>>(which, n, n_pad, lines,
@@ -2101,7 +2140,7 @@ static int finish_payloads_dev(bn254_ctx* ctx, const uint8_t* payloads, size_t m
   DALLOC(FIOf, sizeof(u4) * 6 * 2 * 2 * COOP_LANES);
   DALLOC(GSf, sizeof(u4) * COOP_GSLOTS * 6 * 2 * 2 * COOP_LANES);
   LAUNCH(k_finish_prepare, 1, BN_BLOCK, payloads, (int)m, agg_sig, ctx->d_lines, LNf.as<u4>(), FIOf.as<u4>(), status);
-  k_coop_run<<<1, COOP_THREADS, COOP_SMEM_BYTES, ctx->stream>>>(CPROG_FINISH, (size_t)1, (size_t)COOP_LANES, LNf.as<u4>(), GSf.as<u4>(), FIOf.as<u4>(), status,
+  k_coop_run<<<1, COOP_THREADS, COOP1_SMEM_BYTES, ctx->stream>>>(CPROG_FINISH, (size_t)1, (size_t)COOP_LANES, LNf.as<u4>(), GSf.as<u4>(), FIOf.as<u4>(), status,
                                                                 0u, (unsigned)ctx->sm_count);
   ctx->launches++;
   CK(cudaGetLastError());

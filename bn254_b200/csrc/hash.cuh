@@ -64,7 +64,8 @@ BN_FN void sha256_init(uint32_t* s) {
 // receives the accepted counter.  max_tries is 255 (/root/reference/src/hash.rs:39: `for ctr in 0..255`); a smaller
 // value exists only so that tests can reach the HashToPointError exit (/root/reference/src/hash.rs:62), which no
 // real message does (2^-235).
-BN_NOINLINE int hash_to_g1(fq* hx, fq* hy, const uint8_t* msg, uint64_t len, int* ctr_out, int max_tries = 255) {
+// Counters ctr_first .. max_tries - 1 are tried (ctr_first > 0: the warp-parallel batch kernel, where lane l of a warp owns one counter).
+BN_NOINLINE int hash_to_g1(fq* hx, fq* hy, const uint8_t* msg, uint64_t len, int* ctr_out, int max_tries = 255, int ctr_first = 0) {
   // midstate over the full 64-byte blocks of msg
   uint32_t mid[8], blk[16];
   sha256_init(mid);
@@ -91,7 +92,7 @@ BN_NOINLINE int hash_to_g1(fq* hx, fq* hy, const uint8_t* msg, uint64_t len, int
   const int cw = rem >> 2, cs = 24 - 8 * (rem & 3);
   const uint32_t base_word = tail[cw];
 
-  for (int ctr = 0; ctr < max_tries; ctr++) {
+  for (int ctr = ctr_first; ctr < max_tries; ctr++) {
     uint32_t st[8];
     for (int i = 0; i < 8; i++) st[i] = mid[i];
     tail[cw] = base_word | ((uint32_t)ctr << cs);
