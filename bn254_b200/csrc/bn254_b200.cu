@@ -406,17 +406,7 @@ __global__ void __launch_bounds__(COOP_THREADS, BN_COOP_MINB) k_coop_run(int whi
   c.gslots = gslots;
   c.fio = fio;
   c.status = status;
-  const uint32_t* prog = coop_program(which);
-  int line_next = 0;
-#pragma unroll 1
-  for (int pc = 0;; pc++) {
-    const uint32_t ins = prog[pc];
-    if ((ins & 0xff) == COP_END) break;
-    fq2 t = coop_phase_a(c, ins, line_next);
-    COOP_BARRIER();
-    coop_phase_b(c, ins, t, line_next);
-    COOP_BARRIER();
-  }
+  coop_run_block(c, coop_program(which), [] { COOP_BARRIER(); });
 }
 
 // ---- the same block-layout machine with FOUR 32-item groups in one 24-warp block (one block per SM).  Warp w of a block
@@ -445,7 +435,8 @@ __global__ void __launch_bounds__(COOP4_THREADS, 1) k_coop4_run(int which, size_
   c.row = COOP_LANES;
   c.wmode = false;
   c.plans = K_COOP_PLANS;
-  c.kq = (stagger_ns & 0x80000000u) ? nullptr : kq;  // tuning switch: top bit of the knob selects the additions-only xi variants
+  c.kq = kq;
+  (void)stagger_ns;  // (round-1 tuning knob: start offsets between the warps of a group -- measured slower, removed from the loop)
   c.item = ((size_t)blockIdx.x * COOP4_GROUPS + g) * COOP_LANES + c.lane;
   c.active = c.item < n;
   c.n_pad = n_pad;
@@ -453,24 +444,8 @@ __global__ void __launch_bounds__(COOP4_THREADS, 1) k_coop4_run(int which, size_
   c.gslots = gslots;
   c.fio = fio;
   c.status = status;
-  const uint32_t* prog = coop_program(which);
-  int line_next = 0;
   const int bar = g + 1;
-#pragma unroll 1
-  for (int pc = 0;; pc++) {
-    const uint32_t ins = prog[pc];
-    if ((ins & 0xff) == COP_END) break;
-    // The six warps of a group leave the barrier together and the scheduler keeps them in step, so their multiply-free
-    // stretches (operand loads, reduction fix-ups, recombination) would coincide and leave the multiplier pipe idle while
-    // the ALU pipe is busy, and vice versa.  One warp in its accumulation phase saturates the pipe on its own, so warp k
-    // starts k * stagger_ns late: the warps stay offset through the phase and each one's ALU work hides under another's
-    // multiply-adds; the early finishers simply wait at the barrier.
-    if ((stagger_ns & 0x7fffffffu) && (ins & 0xff) == COP_DOT && c.k) __nanosleep(c.k * (stagger_ns & 0x7fffffffu));
-    fq2 t = coop_phase_a(c, ins, line_next);
-    asm volatile("bar.sync %0, %1;" ::"r"(bar), "n"(COOP_THREADS) : "memory");
-    coop_phase_b(c, ins, t, line_next);
-    asm volatile("bar.sync %0, %1;" ::"r"(bar), "n"(COOP_THREADS) : "memory");
-  }
+  coop_run_block(c, coop_program(which), [bar] { asm volatile("bar.sync %0, %1;" ::"r"(bar), "n"(COOP_THREADS) : "memory"); });
 }
 
 // ---- half-warp layout: a group is 16 items and THREE warps, each warp carrying two coefficients (lanes 0-15 one, lanes

@@ -89,19 +89,49 @@ BN_FN uint32_t u256_sub(uint32_t* r, const uint32_t* a, const uint32_t* b) {
 
 // ------------------------------------------------------------------------------------------------ add / sub
 #if defined(__CUDA_ARCH__)
-BN_FN fq fq_add(const fq& a, const fq& b) {
-  uint32_t s0, s1, s2, s3, s4, s5, s6, s7, t0, t1, t2, t3, t4, t5, t6, t7, bw;
-  asm("add.cc.u32 %0, %8, %16;\n\t"
-      "addc.cc.u32 %1, %9, %17;\n\t"
-      "addc.cc.u32 %2, %10, %18;\n\t"
-      "addc.cc.u32 %3, %11, %19;\n\t"
-      "addc.cc.u32 %4, %12, %20;\n\t"
-      "addc.cc.u32 %5, %13, %21;\n\t"
-      "addc.cc.u32 %6, %14, %22;\n\t"
-      "addc.u32 %7, %15, %23;\n\t"
-      : "=&r"(s0), "=&r"(s1), "=&r"(s2), "=&r"(s3), "=&r"(s4), "=&r"(s5), "=&r"(s6), "=&r"(s7)
-      : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]),
-        "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
+// a >= q decided by the top limb; the full comparison runs only when the top limbs are equal (probability 2^-32 for field
+// values), out of line, so that the common path is two compares and a branch that is never taken
+__device__ __noinline__ uint32_t fq_geq_q_slow(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4, uint32_t a5, uint32_t a6) {
+  uint32_t bw;
+  asm("{\n\t.reg .u32 t;\n\t"
+      "sub.cc.u32 t, %1, 0xd87cfd47;\n\t"
+      "subc.cc.u32 t, %2, 0x3c208c16;\n\t"
+      "subc.cc.u32 t, %3, 0x6871ca8d;\n\t"
+      "subc.cc.u32 t, %4, 0x97816a91;\n\t"
+      "subc.cc.u32 t, %5, 0x8181585d;\n\t"
+      "subc.cc.u32 t, %6, 0xb85045b6;\n\t"
+      "subc.cc.u32 t, %7, 0xe131a029;\n\t"
+      "subc.u32 %0, 0, 0;\n\t}"
+      : "=r"(bw)
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(a4), "r"(a5), "r"(a6));
+  return bw == 0;  // no borrow: the low seven limbs are >= those of q
+}
+// conditional subtraction: a in [0, 2^256) -> a - q if a >= q else a.  The subtraction is PREDICATED (eight instructions that
+// do nothing when a < q) instead of computed-then-selected (eight subtractions, a borrow and eight selects): the kernels on this
+// path are bound by the number of instructions they issue (profiles/r02_tuning_log.md), and every modular addition /
+// subtraction / reduction ends in one of these.
+#if defined(BN_FQ_PRED_CSUB)
+BN_FN fq fq_csub(const fq& a) {
+  uint32_t ge = a.l[7] > BN_Q7 ? 1u : 0u;
+  if (a.l[7] == BN_Q7) ge = fq_geq_q_slow(a.l[0], a.l[1], a.l[2], a.l[3], a.l[4], a.l[5], a.l[6]);
+  fq r = a;
+  asm("{\n\t.reg .pred p;\n\t"
+      "setp.ne.u32 p, %8, 0;\n\t"
+      "@p sub.cc.u32 %0, %0, 0xd87cfd47;\n\t"
+      "@p subc.cc.u32 %1, %1, 0x3c208c16;\n\t"
+      "@p subc.cc.u32 %2, %2, 0x6871ca8d;\n\t"
+      "@p subc.cc.u32 %3, %3, 0x97816a91;\n\t"
+      "@p subc.cc.u32 %4, %4, 0x8181585d;\n\t"
+      "@p subc.cc.u32 %5, %5, 0xb85045b6;\n\t"
+      "@p subc.cc.u32 %6, %6, 0xe131a029;\n\t"
+      "@p subc.u32 %7, %7, 0x30644e72;\n\t}"
+      : "+r"(r.l[0]), "+r"(r.l[1]), "+r"(r.l[2]), "+r"(r.l[3]), "+r"(r.l[4]), "+r"(r.l[5]), "+r"(r.l[6]), "+r"(r.l[7])
+      : "r"(ge));
+  return r;
+}
+#else
+BN_FN fq fq_csub(const fq& a) {
+  uint32_t t0, t1, t2, t3, t4, t5, t6, t7, bw;
   asm("sub.cc.u32 %0, %9, 0xd87cfd47;\n\t"
       "subc.cc.u32 %1, %10, 0x3c208c16;\n\t"
       "subc.cc.u32 %2, %11, 0x6871ca8d;\n\t"
@@ -112,13 +142,58 @@ BN_FN fq fq_add(const fq& a, const fq& b) {
       "subc.cc.u32 %7, %16, 0x30644e72;\n\t"
       "subc.u32 %8, 0, 0;\n\t"
       : "=&r"(t0), "=&r"(t1), "=&r"(t2), "=&r"(t3), "=&r"(t4), "=&r"(t5), "=&r"(t6), "=&r"(t7), "=&r"(bw)
-      : "r"(s0), "r"(s1), "r"(s2), "r"(s3), "r"(s4), "r"(s5), "r"(s6), "r"(s7));
+      : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]));
   fq r;
-  bool keep = bw != 0;  // borrow: a + b < q
-  r.l[0] = keep ? s0 : t0; r.l[1] = keep ? s1 : t1; r.l[2] = keep ? s2 : t2; r.l[3] = keep ? s3 : t3;
-  r.l[4] = keep ? s4 : t4; r.l[5] = keep ? s5 : t5; r.l[6] = keep ? s6 : t6; r.l[7] = keep ? s7 : t7;
+  const bool keep = bw != 0;  // borrow: a < q
+  r.l[0] = keep ? a.l[0] : t0; r.l[1] = keep ? a.l[1] : t1; r.l[2] = keep ? a.l[2] : t2; r.l[3] = keep ? a.l[3] : t3;
+  r.l[4] = keep ? a.l[4] : t4; r.l[5] = keep ? a.l[5] : t5; r.l[6] = keep ? a.l[6] : t6; r.l[7] = keep ? a.l[7] : t7;
   return r;
 }
+#endif
+BN_FN fq fq_add(const fq& a, const fq& b) {
+  fq s;
+  asm("add.cc.u32 %0, %8, %16;\n\t"
+      "addc.cc.u32 %1, %9, %17;\n\t"
+      "addc.cc.u32 %2, %10, %18;\n\t"
+      "addc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\t"
+      "addc.cc.u32 %5, %13, %21;\n\t"
+      "addc.cc.u32 %6, %14, %22;\n\t"
+      "addc.u32 %7, %15, %23;\n\t"
+      : "=&r"(s.l[0]), "=&r"(s.l[1]), "=&r"(s.l[2]), "=&r"(s.l[3]), "=&r"(s.l[4]), "=&r"(s.l[5]), "=&r"(s.l[6]), "=&r"(s.l[7])
+      : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]),
+        "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
+  return fq_csub(s);  // a + b < 2 q < 2^255: no carry out of the top limb
+}
+#if !defined(BN_FQ_SEL_SUB)  // predicated add-back: 19 instructions instead of 25 (-0.35 % k_coop4_run, -2.9 % k_verify_lines, A/B r02)
+BN_FN fq fq_sub(const fq& a, const fq& b) {
+  fq r;
+  // a - b, then + q under the borrow's predicate
+  asm("{\n\t.reg .pred p;\n\t.reg .u32 m;\n\t"
+      "sub.cc.u32 %0, %8, %16;\n\t"
+      "subc.cc.u32 %1, %9, %17;\n\t"
+      "subc.cc.u32 %2, %10, %18;\n\t"
+      "subc.cc.u32 %3, %11, %19;\n\t"
+      "subc.cc.u32 %4, %12, %20;\n\t"
+      "subc.cc.u32 %5, %13, %21;\n\t"
+      "subc.cc.u32 %6, %14, %22;\n\t"
+      "subc.cc.u32 %7, %15, %23;\n\t"
+      "subc.u32 m, 0, 0;\n\t"
+      "setp.ne.u32 p, m, 0;\n\t"
+      "@p add.cc.u32 %0, %0, 0xd87cfd47;\n\t"
+      "@p addc.cc.u32 %1, %1, 0x3c208c16;\n\t"
+      "@p addc.cc.u32 %2, %2, 0x6871ca8d;\n\t"
+      "@p addc.cc.u32 %3, %3, 0x97816a91;\n\t"
+      "@p addc.cc.u32 %4, %4, 0x8181585d;\n\t"
+      "@p addc.cc.u32 %5, %5, 0xb85045b6;\n\t"
+      "@p addc.cc.u32 %6, %6, 0xe131a029;\n\t"
+      "@p addc.u32 %7, %7, 0x30644e72;\n\t}"
+      : "=&r"(r.l[0]), "=&r"(r.l[1]), "=&r"(r.l[2]), "=&r"(r.l[3]), "=&r"(r.l[4]), "=&r"(r.l[5]), "=&r"(r.l[6]), "=&r"(r.l[7])
+      : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]),
+        "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
+  return r;
+}
+#else
 BN_FN fq fq_sub(const fq& a, const fq& b) {
   uint32_t d0, d1, d2, d3, d4, d5, d6, d7, m;
   asm("sub.cc.u32 %0, %9, %17;\n\t"
@@ -147,6 +222,7 @@ BN_FN fq fq_sub(const fq& a, const fq& b) {
         "r"(m & BN_Q0), "r"(m & BN_Q1), "r"(m & BN_Q2), "r"(m & BN_Q3), "r"(m & BN_Q4), "r"(m & BN_Q5), "r"(m & BN_Q6), "r"(m & BN_Q7));
   return r;
 }
+#endif
 #else
 BN_FN fq fq_add(const fq& a, const fq& b) {
   fq s, t;
@@ -172,30 +248,6 @@ BN_FN fq fq_sub(const fq& a, const fq& b) {
   }
   return d;
 }
-#endif
-BN_FN fq fq_dbl(const fq& a) { return fq_add(a, a); }
-// conditional subtraction: a in [0, 2^256) -> a - q if a >= q else a
-#if defined(__CUDA_ARCH__)
-BN_FN fq fq_csub(const fq& a) {
-  uint32_t t0, t1, t2, t3, t4, t5, t6, t7, bw;
-  asm("sub.cc.u32 %0, %9, 0xd87cfd47;\n\t"
-      "subc.cc.u32 %1, %10, 0x3c208c16;\n\t"
-      "subc.cc.u32 %2, %11, 0x6871ca8d;\n\t"
-      "subc.cc.u32 %3, %12, 0x97816a91;\n\t"
-      "subc.cc.u32 %4, %13, 0x8181585d;\n\t"
-      "subc.cc.u32 %5, %14, 0xb85045b6;\n\t"
-      "subc.cc.u32 %6, %15, 0xe131a029;\n\t"
-      "subc.cc.u32 %7, %16, 0x30644e72;\n\t"
-      "subc.u32 %8, 0, 0;\n\t"
-      : "=&r"(t0), "=&r"(t1), "=&r"(t2), "=&r"(t3), "=&r"(t4), "=&r"(t5), "=&r"(t6), "=&r"(t7), "=&r"(bw)
-      : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]));
-  fq r;
-  const bool keep = bw != 0;  // borrow: a < q
-  r.l[0] = keep ? a.l[0] : t0; r.l[1] = keep ? a.l[1] : t1; r.l[2] = keep ? a.l[2] : t2; r.l[3] = keep ? a.l[3] : t3;
-  r.l[4] = keep ? a.l[4] : t4; r.l[5] = keep ? a.l[5] : t5; r.l[6] = keep ? a.l[6] : t6; r.l[7] = keep ? a.l[7] : t7;
-  return r;
-}
-#else
 BN_FN fq fq_csub(const fq& a) {
   fq t;
   const uint32_t qq[8] = {BN_Q0, BN_Q1, BN_Q2, BN_Q3, BN_Q4, BN_Q5, BN_Q6, BN_Q7};
@@ -204,6 +256,7 @@ BN_FN fq fq_csub(const fq& a) {
   return t;
 }
 #endif
+BN_FN fq fq_dbl(const fq& a) { return fq_add(a, a); }
 BN_FN fq fq_neg(const fq& a) { return fq_sub(fq_zero(), a); }
 
 #define BN_KQ_RECIP 0xa948e8c0u /* floor(2^59 / ((q >> 226) + 1)) */
@@ -465,7 +518,7 @@ BN_FN void mont_reduce_row(uint32_t* Y, uint32_t* X) {
 }
 // final merge + conditional subtraction: res[k] = X[k] + Y[k+1]; value < 2q
 BN_FN fq mont_finish(const uint32_t* X, const uint32_t* Y) {
-  uint32_t s0, s1, s2, s3, s4, s5, s6, s7, t0, t1, t2, t3, t4, t5, t6, t7, bw;
+  fq s;
   asm("add.cc.u32 %0, %8, %16;\n\t"
       "addc.cc.u32 %1, %9, %17;\n\t"
       "addc.cc.u32 %2, %10, %18;\n\t"
@@ -474,25 +527,10 @@ BN_FN fq mont_finish(const uint32_t* X, const uint32_t* Y) {
       "addc.cc.u32 %5, %13, %21;\n\t"
       "addc.cc.u32 %6, %14, %22;\n\t"
       "addc.u32 %7, %15, 0;\n\t"
-      : "=&r"(s0), "=&r"(s1), "=&r"(s2), "=&r"(s3), "=&r"(s4), "=&r"(s5), "=&r"(s6), "=&r"(s7)
+      : "=&r"(s.l[0]), "=&r"(s.l[1]), "=&r"(s.l[2]), "=&r"(s.l[3]), "=&r"(s.l[4]), "=&r"(s.l[5]), "=&r"(s.l[6]), "=&r"(s.l[7])
       : "r"(X[0]), "r"(X[1]), "r"(X[2]), "r"(X[3]), "r"(X[4]), "r"(X[5]), "r"(X[6]), "r"(X[7]),
         "r"(Y[1]), "r"(Y[2]), "r"(Y[3]), "r"(Y[4]), "r"(Y[5]), "r"(Y[6]), "r"(Y[7]));
-  asm("sub.cc.u32 %0, %9, 0xd87cfd47;\n\t"
-      "subc.cc.u32 %1, %10, 0x3c208c16;\n\t"
-      "subc.cc.u32 %2, %11, 0x6871ca8d;\n\t"
-      "subc.cc.u32 %3, %12, 0x97816a91;\n\t"
-      "subc.cc.u32 %4, %13, 0x8181585d;\n\t"
-      "subc.cc.u32 %5, %14, 0xb85045b6;\n\t"
-      "subc.cc.u32 %6, %15, 0xe131a029;\n\t"
-      "subc.cc.u32 %7, %16, 0x30644e72;\n\t"
-      "subc.u32 %8, 0, 0;\n\t"
-      : "=&r"(t0), "=&r"(t1), "=&r"(t2), "=&r"(t3), "=&r"(t4), "=&r"(t5), "=&r"(t6), "=&r"(t7), "=&r"(bw)
-      : "r"(s0), "r"(s1), "r"(s2), "r"(s3), "r"(s4), "r"(s5), "r"(s6), "r"(s7));
-  fq r;
-  bool keep = bw != 0;
-  r.l[0] = keep ? s0 : t0; r.l[1] = keep ? s1 : t1; r.l[2] = keep ? s2 : t2; r.l[3] = keep ? s3 : t3;
-  r.l[4] = keep ? s4 : t4; r.l[5] = keep ? s5 : t5; r.l[6] = keep ? s6 : t6; r.l[7] = keep ? s7 : t7;
-  return r;
+  return fq_csub(s);
 }
 }  // namespace detail
 

@@ -1,11 +1,11 @@
-#!/bin/bash
-# A/B of an environment knob in one session: usage gpu_ab.sh VAR v1 v2 ... (full 2^20 bench per value, two rounds)
-var=$1; shift
+# A/B of tuning builds: scripts/gpu_ab.sh name1 name2 ...  (variants/lib_<name>.so), twice each, n = 2^18
+mkdir -p gpurun_out
 for rep in 1 2; do
 for v in "$@"; do
-  echo -n "$var=$v "
-  env $var=$v timeout 600 python bench.py --steps 3 --warmup 2 --cpu-sample 16 2>&1 | tail -1 | python -c "
+  BN254_B200_LIB=$PWD/variants/lib_$v.so python bench.py --n 262144 --steps 2 --warmup 2 --no-extras --cpu-sample 16 2>/dev/null | python -c "
 import json,sys
-d=json.loads(sys.stdin.read()); r=d['roofline']
-print(json.dumps({'value':round(d['value']),'e2e':round(d['e2e']['value']),'ms':round(d['ms_per_step'],2),'phase_ms':{k:round(v,1) for k,v in r['phase_ms'].items()}}))"
-done; done
+d=json.loads(sys.stdin.read().strip().splitlines()[-1])
+p=d['roofline']['phase_ms']
+print('$v rep$rep value %.0f hash %.2f lines %.2f machine %.2f' % (d['value'], p['hash_to_g1'], p['line_sets'], p['miller_and_final_exp']))"
+done
+done

@@ -249,6 +249,25 @@ struct coop_sim {
         for (int l = 0; l < lanes; l++) coop_invt(sm.data() + l, row);
         continue;
       }
+      if (g_coop_wmode == 0 && (ins & 0xff) == COP_DOT) {
+        // block layout: the fast path the device kernels run (coop_run_block): fetch, coop_dot_block_any, barrier, coop_commit_block
+        const int plan = (ins >> 8) & 0xff;
+        for (int l = 0; l < lanes; l++)
+          for (int k = 0; k < COOP_WARPS; k++) {
+            coop_ctx c = ctx(k, l);
+            if ((ins >> 16) & 1) {
+              coop_line_fetch(c, line_next[k][l], line_next[k][l] & 1);
+              line_next[k][l]++;
+            }
+            t[k * COOP_LANES + l] = coop_dot_block_any(c.sm, plan, k);
+          }
+        for (int l = 0; l < lanes; l++)
+          for (int k = 0; k < COOP_WARPS; k++) {
+            coop_ctx c = ctx(k, l);
+            coop_commit_block(c.sm, k, K_COOP_PLANS[plan][k][0], t[k * COOP_LANES + l], (ins >> 25) & 0x3f, c.kq);
+          }
+        continue;
+      }
       for (int l = 0; l < lanes; l++)
         for (int k = 0; k < COOP_WARPS; k++) t[k * COOP_LANES + l] = coop_phase_a(ctx(k, l), ins, line_next[k][l]);
       for (int l = 0; l < lanes; l++)
