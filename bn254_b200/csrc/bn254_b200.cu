@@ -1361,17 +1361,31 @@ int bn254_sign_batch(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, const 
 // sub-partition, k_coop4_run) unless the context asks for the one-group-per-block kernel (pairing mode 2)
 static int launch_coop_groups(bn254_ctx* ctx, int which, size_t n, size_t n_pad, const u4* lines, u4* gslots, u4* fio, uint8_t* status,
                               size_t groups) {
-  // Fewer groups than one full wave of four-group blocks: one group per six-warp block instead, so that the groups spread over
-  // all SMs and a group's warps over the four sub-partitions of its SM -- the latency of a one-item verify drops from 7.6 ms to
-  // about 3 ms in the machine.  (At full load the four-group block is 5 % faster: profiles/r01_tuning_log.md.)
-  const bool small = groups < (size_t)ctx->sm_count * COOP4_GROUPS;
-  if (ctx->pairing_mode == 2 || !ctx->coop_groups4 || small)
-    k_coop_run<<<(unsigned)groups, COOP_THREADS, COOP1_SMEM_BYTES, ctx->stream>>>(which, n, n_pad, lines, gslots, fio, status, ctx->coop_stagger,
-                                                                                (unsigned)ctx->sm_count);
-  else
-    k_coop4_run<<<(unsigned)((groups + COOP4_GROUPS - 1) / COOP4_GROUPS), COOP4_THREADS, COOP4_SMEM_BYTES, ctx->stream>>>(which, n, n_pad, lines,
-                                                                                                                        gslots, fio, status,
-                                                                                                                        ctx->coop_stagger);
+  const size_t sms = (size_t)ctx->sm_count;
+  auto one_group_blocks = [&](size_t g0, size_t cnt) {  // groups g0 .. g0 + cnt - 1, one six-warp block each
+    const size_t i0 = g0 * COOP_LANES;
+    k_coop_run<<<(unsigned)cnt, COOP_THREADS, COOP1_SMEM_BYTES, ctx->stream>>>(which, n > i0 ? n - i0 : 0, n_pad, lines + i0, gslots ? gslots + i0 : gslots,
+                                                                            fio ? fio + i0 : fio, status ? status + i0 : status, ctx->coop_stagger,
+                                                                            (unsigned)sms);
+    ctx->launches++;
+  };
+  if (ctx->pairing_mode == 2 || !ctx->coop_groups4) {
+    one_group_blocks(0, groups);
+    CK(cudaGetLastError());
+    return 0;
+  }
+  // Default: four groups per 24-warp block (one group per sub-partition).  Launches of at most two groups per SM use one-group
+  // blocks instead: the groups spread over all SMs and a group's six warps over the four sub-partitions of its SM (2 + 2 + 1 + 1),
+  // and the machine's share of a one-item verify drops from 7.6 ms to 3.1 ms.  (From three one-group blocks per SM on, two
+  // sub-partitions carry six warps again and the four-group block is the faster layout.  Cutting big launches into whole waves
+  // plus a one-group tail was measured too: +5 %, the tail blocks run two deep.)
+  if (groups <= 2 * sms) {
+    one_group_blocks(0, groups);
+    CK(cudaGetLastError());
+    return 0;
+  }
+  k_coop4_run<<<(unsigned)((groups + COOP4_GROUPS - 1) / COOP4_GROUPS), COOP4_THREADS, COOP4_SMEM_BYTES, ctx->stream>>>(which, n, n_pad, lines, gslots,
+                                                                                                                      fio, status, ctx->coop_stagger);
   ctx->launches++;
   CK(cudaGetLastError());
   return 0;

@@ -390,8 +390,21 @@ BN_FN fq fq_3t_2z(const fq& t, const fq& z, const uint32_t* kq) {
 // q - a as a plain integer (a <= q - 1 gives 1..q; a == 0 gives q itself, which fq_mul9_add accepts as its z)
 BN_FN fq fq_q_minus(const fq& a) {
   fq r;
+#if defined(__CUDA_ARCH__)
+  asm("sub.cc.u32 %0, 0xd87cfd47, %8;\n\t"
+      "subc.cc.u32 %1, 0x3c208c16, %9;\n\t"
+      "subc.cc.u32 %2, 0x6871ca8d, %10;\n\t"
+      "subc.cc.u32 %3, 0x97816a91, %11;\n\t"
+      "subc.cc.u32 %4, 0x8181585d, %12;\n\t"
+      "subc.cc.u32 %5, 0xb85045b6, %13;\n\t"
+      "subc.cc.u32 %6, 0xe131a029, %14;\n\t"
+      "subc.u32 %7, 0x30644e72, %15;\n\t"
+      : "=&r"(r.l[0]), "=&r"(r.l[1]), "=&r"(r.l[2]), "=&r"(r.l[3]), "=&r"(r.l[4]), "=&r"(r.l[5]), "=&r"(r.l[6]), "=&r"(r.l[7])
+      : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]));
+#else
   const uint32_t qq[8] = {BN_Q0, BN_Q1, BN_Q2, BN_Q3, BN_Q4, BN_Q5, BN_Q6, BN_Q7};
   u256_sub(r.l, qq, a.l);
+#endif
   return r;
 }
 

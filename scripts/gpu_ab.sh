@@ -2,7 +2,7 @@
 mkdir -p gpurun_out
 for rep in 1 2; do
 for v in "$@"; do
-  BN254_B200_LIB=$PWD/variants/lib_$v.so python bench.py --n 262144 --steps 2 --warmup 2 --no-extras --cpu-sample 16 2>/dev/null | python -c "
+  BN254_B200_LIB=$PWD/variants/lib_$v.so python bench.py --n ${N:-262144} --steps 2 --warmup 2 --no-extras --cpu-sample 16 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
 p=d['roofline']['phase_ms']
