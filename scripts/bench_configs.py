@@ -33,6 +33,7 @@ def timed(ctx, fn, reps=3):
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
     ctx = E.context(0)
+    E.set_input_policy(E.INPUTS_TYPED, ctx=ctx)  # values of the crate's types, like the bench line
     dev = lambda b: torch.frombuffer(bytearray(b), dtype=torch.uint8).cuda()
     msgs, sks = synth.messages(n, 32, seed=1), synth.secret_keys(n, seed=2)
     d_msgs, d_sks = dev(msgs), dev(sks)
