@@ -13,6 +13,7 @@ SYMBOLS = [
     "bn254_hash_to_g1_batch", "bn254_hash_to_g1_batch_dev", "bn254_hash_to_g1_var",
     "bn254_sign_batch", "bn254_sign_batch_dev", "bn254_verify_batch", "bn254_verify_batch_dev",
     "bn254_verify_batch_rlc", "bn254_verify_batch_rlc_dev",
+    "bn254_key_lines_bytes", "bn254_key_lines_prepare_dev", "bn254_verify_batch_cached_dev",
     "bn254_check_public_keys_batch", "bn254_pairing_check_batch", "bn254_pairing_check_batch_dev",
     "bn254_g1_sum", "bn254_g2_sum", "bn254_g1_sum_dev", "bn254_g2_sum_dev",
     "bn254_derive_pk_g2_batch", "bn254_derive_pk_g1_batch", "bn254_g1_mul_batch", "bn254_g2_mul_batch",
@@ -48,6 +49,8 @@ def load():
         lib.bn254_ctx_destroy.restype = None
         lib.bn254_sync.argtypes = [ctypes.c_void_p]
         lib.bn254_get_input_policy.argtypes = [ctypes.c_void_p]
+        lib.bn254_key_lines_bytes.restype = ctypes.c_size_t
+        lib.bn254_key_lines_bytes.argtypes = [ctypes.c_size_t]
         _lib = lib
     return _lib
 

@@ -638,6 +638,61 @@ __global__ void __launch_bounds__(BN_BLOCK, BN_LINES_MINB) k_item_pair_lines(con
   }
   item_pair_lines(lines, n_pad, i, s, k, use, &h, q.x, q.y, &consts[threadIdx.x]);
 }
+// ---- cached key lines (a fixed validator set): the walk of every key once, then per verify only the scaling
+// kstatus[j] = decode status of key j under the context's input policy (untrusted: from_uncompressed semantics, r-torsion test)
+__global__ void __launch_bounds__(BN_BLOCK, BN_LINES_MINB) k_key_lines(const uint8_t* __restrict__ pks, size_t n_keys, size_t k_pad, int typed,
+                                                                       u4* __restrict__ klines, uint8_t* __restrict__ kstatus) {
+  __shared__ lines_consts consts[BN_BLOCK];
+  size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_keys) return;
+  g2j q;
+  int st = typed ? ST_OK : item_g2_validate(pks + 128 * j);
+  if (!st) st = g2_from_raw(&q, pks + 128 * j);
+  kstatus[j] = (uint8_t)st;
+  const bool use = !st && !pt_is_inf(&q);
+  if (!use) {
+    q.x = fq2_one();
+    q.y = fq2_one();
+  }
+  item_key_lines(klines, k_pad, j, use, q.x, q.y, &consts[threadIdx.x]);
+}
+// per item: key index / key status / signature decode -> status (precedence of verify_batch: under the untrusted policy a decode
+// error replaces a hash error, under the typed policy the hash error stays) and the signature in Montgomery form ((0, 0) = infinity)
+__global__ void __launch_bounds__(BN_BLOCK) k_cached_decode(const uint8_t* __restrict__ sigs, size_t n, const uint32_t* __restrict__ key_index,
+                                                            size_t key_base, size_t n_keys, const uint8_t* __restrict__ kstatus, int typed,
+                                                            g1aff* __restrict__ S, uint8_t* __restrict__ status) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const size_t key = key_index ? key_index[i] : key_base + i;  // (identity mapping: the chunk's first item is key `key_base`)
+  int st = key >= n_keys ? ST_INDEX_OOB : kstatus[key];
+  g1j s;
+  pt_set_inf(&s);
+  if (!st && !typed) st = item_g1_validate(sigs + 64 * i);
+  if (!st) st = g1_from_raw(&s, sigs + 64 * i);
+  g1aff o;
+  o.x = fq_zero();
+  o.y = fq_zero();
+  if (!st && !pt_is_inf(&s)) {
+    o.x = s.x;
+    o.y = s.y;
+  }
+  S[i] = o;
+  if (st && (!typed || !status[i])) status[i] = (uint8_t)st;
+}
+// one thread per (line m, item): thread index = m * n_pad + item, so that a warp writes 32 neighbouring items of one line set
+__global__ void __launch_bounds__(BN_BLOCK) k_scale_cached_lines(const g1aff* __restrict__ H, const g1aff* __restrict__ S, size_t n, size_t n_pad,
+                                                                 const u4* __restrict__ klines, size_t k_pad, const uint32_t* __restrict__ key_index,
+                                                                 size_t key_base, u4* __restrict__ lines, const uint8_t* __restrict__ status,
+                                                                 const line_t* __restrict__ table) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t item = t % n_pad;
+  const int m = (int)(t / n_pad);
+  if (m >= K_N_LINES || item >= n || status[item]) return;
+  const size_t key = key_index ? key_index[item] : key_base + item;
+  const g1aff s = S[item];
+  item_scale_cached_lines(lines, n_pad, item, m, klines, k_pad, key, H[item], !(fq_is_zero(s.x) && fq_is_zero(s.y)), s.x, s.y, table);
+}
+
 // lane 0 of every block holds the block's product (power-basis layout fio) -> tower-order Fq12 array
 __global__ void k_coop_gather(const u4* __restrict__ fio, size_t L, size_t blocks, fq12* __restrict__ out) {
   size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1478,6 +1533,79 @@ static int verify_dev_impl(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, 
     }
   }
   return 0;
+}
+// ---- verify against cached key lines (bn254_key_lines_prepare_dev): hash, scaling of the cached / fixed lines, the machine
+static int verify_cached_dev_impl(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, const uint8_t* sigs, const u4* klines,
+                                  const uint8_t* kstatus, size_t n_keys, const uint32_t* key_index, size_t n, uint8_t* status) {
+  const size_t k_pad = (n_keys + COOP_LANES - 1) / COOP_LANES * COOP_LANES;
+  size_t CHUNK = (size_t)1 << ctx->chunk_log2;
+  const int typed = ctx->input_policy == BN254_INPUTS_TYPED ? 1 : 0;
+  DALLOC(H, sizeof(g1aff) * n);
+  DALLOC(SG, sizeof(g1aff) * (n < CHUNK ? n : CHUNK));
+  dbuf LN(ctx), GS(ctx);
+  for (;;) {
+    size_t cap = n < CHUNK ? n : CHUNK;
+    size_t cap_pad = (cap + COOP_LANES - 1) / COOP_LANES * COOP_LANES;
+    cudaError_t e2 = LN.alloc(sizeof(u4) * 2 * COOP_LINE_FQ * 2 * K_N_LINES * cap_pad);
+    cudaError_t e3 = e2 == cudaSuccess ? GS.alloc(sizeof(u4) * COOP_GSLOTS * 6 * 2 * 2 * cap_pad) : e2;
+    if (e3 == cudaSuccess) break;
+    cudaGetLastError();
+    LN.release();
+    GS.release();
+    if (e3 != cudaErrorMemoryAllocation || CHUNK <= 1024) {
+      ctx->err = std::string("verify workspace allocation failed: ") + cudaGetErrorString(e3);
+      return e3 == cudaErrorMemoryAllocation ? BN254_E_NOMEM : BN254_E_CUDA;
+    }
+    CHUNK >>= 1;
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemPoolTrimTo(ctx->pool, 0));
+  }
+  auto mark = [&]() -> cudaError_t {
+    if (!ctx->prof) return cudaSuccess;
+    cudaEvent_t ev;
+    cudaError_t e = cudaEventCreate(&ev);
+    if (e != cudaSuccess) return e;
+    ctx->prof_ev.push_back(ev);
+    return cudaEventRecord(ev, ctx->stream);
+  };
+  for (size_t off = 0; off < n; off += CHUNK) {
+    const size_t m = n - off < CHUNK ? n - off : CHUNK, m_pad = (m + COOP_LANES - 1) / COOP_LANES * COOP_LANES;
+    CK(mark());
+    if (off == 0) {
+      int rc = hash_dev(ctx, msgs, msg_len, nullptr, n, H.as<g1aff>(), status, nullptr);
+      if (rc) return rc;
+    }
+    CK(mark());
+    LAUNCH(k_cached_decode, grid_for(m), BN_BLOCK, sigs + 64 * off, m, key_index ? key_index + off : key_index, off, n_keys, kstatus, typed,
+           SG.as<g1aff>(), status + off);
+    LAUNCH(k_scale_cached_lines, grid_for(m_pad * K_N_LINES), BN_BLOCK, H.as<g1aff>() + off, SG.as<g1aff>(), m, m_pad, klines, k_pad,
+           key_index ? key_index + off : key_index, off, LN.as<u4>(), status + off, ctx->d_lines);
+    CK(mark());
+    int rc = launch_coop_groups(ctx, CPROG_VERIFY, m, m_pad, LN.as<u4>(), GS.as<u4>(), (u4*)nullptr, status + off, m_pad / COOP_LANES);
+    if (rc) return rc;
+    CK(mark());
+  }
+  return 0;
+}
+size_t bn254_key_lines_bytes(size_t n_keys) {
+  const size_t k_pad = (n_keys + COOP_LANES - 1) / COOP_LANES * COOP_LANES;
+  return sizeof(u4) * 2 * COOP_KLINE_FQ * K_N_LINES * (k_pad ? k_pad : COOP_LANES);
+}
+int bn254_key_lines_prepare_dev(bn254_ctx* ctx, const uint8_t* pks, size_t n_keys, uint8_t* key_lines, uint8_t* key_status) {
+  ENTER();
+  if (n_keys == 0) return 0;
+  ARGCHECK(pks && key_lines && key_status && ((uintptr_t)key_lines & 15) == 0);
+  const size_t k_pad = (n_keys + COOP_LANES - 1) / COOP_LANES * COOP_LANES;
+  LAUNCH(k_key_lines, grid_for(n_keys), BN_BLOCK, pks, n_keys, k_pad, ctx->input_policy == BN254_INPUTS_TYPED ? 1 : 0, (u4*)key_lines, key_status);
+  return 0;
+}
+int bn254_verify_batch_cached_dev(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, const uint8_t* sigs, const uint8_t* key_lines,
+                                  const uint8_t* key_status, size_t n_keys, const uint32_t* key_index, size_t n, uint8_t* status) {
+  ENTER();
+  if (n == 0) return 0;
+  ARGCHECK((msgs || msg_len == 0) && sigs && key_lines && key_status && status && n_keys > 0);
+  ARGCHECK(key_index != nullptr || n <= n_keys);
+  return verify_cached_dev_impl(ctx, msgs, msg_len, sigs, (const u4*)key_lines, key_status, n_keys, key_index, n, status);
 }
 int bn254_set_pairing_mode(bn254_ctx* ctx, int mode) {
   ENTER();

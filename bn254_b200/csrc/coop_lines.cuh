@@ -154,4 +154,80 @@ BN_FN void item_pair_lines(u4* lines, size_t n_pad, size_t item, int stream, int
   coop_emit_scaled_v(lines, m * mk + stream, n_pad, item, use, c0, cvw, cvv, K->v[2]);
 }
 
+// ---------------------------------------------------------------------------------------------- cached key lines
+// A public key that verifies many messages (a fixed validator set) needs its walk along the twist only ONCE: the 87 line
+// coefficient triples (ell_0, ell_vw, ell_vv) do not depend on the message.  Layout of the cache (16-byte chunks, key-contiguous):
+//   klines [87 sets][6 Fq][2 chunks][k_pad]      6 Fq = ell_0.c0, ell_0.c1, ell_vw.c0, ell_vw.c1, ell_vv.c0, ell_vv.c1
+// 16 704 bytes per key.  A key at infinity is stored as the constant line 1 (its pair is skipped, as bn::pairing_batch does).
+#define COOP_KLINE_FQ 6
+BN_FN void coop_emit_key_line(u4* klines, size_t set, size_t k_pad, size_t key, bool use, const fq2& ell_0, const fq2& ell_vw, const fq2& ell_vv) {
+  const size_t r = set * COOP_KLINE_FQ;
+  fq2 a = ell_0, b = ell_vw, c = ell_vv;
+  if (!use) {
+    a = fq2_one();
+    b = fq2_zero();
+    c = fq2_zero();
+  }
+  coop_gst(klines, r + 0, k_pad, key, a.c0);
+  coop_gst(klines, r + 1, k_pad, key, a.c1);
+  coop_gst(klines, r + 2, k_pad, key, b.c0);
+  coop_gst(klines, r + 3, k_pad, key, b.c1);
+  coop_gst(klines, r + 4, k_pad, key, c.c0);
+  coop_gst(klines, r + 5, k_pad, key, c.c1);
+}
+// the walk of one key (affine twist point, or `use` == false for a key at infinity / a padding slot)
+BN_FN void item_key_lines(u4* klines, size_t k_pad, size_t key, bool use, const fq2& qx, const fq2& qy, lines_consts* K) {
+  K->v[0] = qx;
+  K->v[1] = qy;
+  fq2 rx = qx, ry = qy, rz = fq2_one();
+  fq2 c0 = fq2_one(), cvw = fq2_zero(), cvv = fq2_zero();
+  size_t m = 0;
+#pragma unroll 1
+  for (int k = 0; k < 64; k++) {
+    if (use) doubling_step_v(rx, ry, rz, c0, cvw, cvv);
+    coop_emit_key_line(klines, m, k_pad, key, use, c0, cvw, cvv);
+    m++;
+    const int d = K_ATE_DIGITS[k];
+    if (d != 0) {
+      if (use) mixed_addition_step_v(K->v[0], d > 0 ? K->v[1] : fq2_neg(K->v[1]), rx, ry, rz, c0, cvw, cvv);
+      coop_emit_key_line(klines, m, k_pad, key, use, c0, cvw, cvv);
+      m++;
+    }
+  }
+  fq2 q1x, q1y, q2x, q2y;
+  g2_frobenius_pair(&q1x, &q1y, &q2x, &q2y, K->v[0], K->v[1]);
+  if (use) mixed_addition_step_v(q1x, q1y, rx, ry, rz, c0, cvw, cvv);
+  coop_emit_key_line(klines, m, k_pad, key, use, c0, cvw, cvv);
+  m++;
+  if (use) mixed_addition_step_v(q2x, q2y, rx, ry, rz, c0, cvw, cvv);
+  coop_emit_key_line(klines, m, k_pad, key, use, c0, cvw, cvv);
+}
+// line sets 2 m and 2 m + 1 of one item from the cache: the key's line m scaled by H(msg), the -G2 table's line m scaled by sig
+BN_FN void item_scale_cached_lines(u4* lines, size_t n_pad, size_t item, int m, const u4* klines, size_t k_pad, size_t key, const g1aff& h,
+                                   bool use_b, const fq& sx, const fq& sy, const line_t* table) {
+  const size_t r = (size_t)m * COOP_KLINE_FQ;
+  fq2 e0, evw, evv;
+  e0.c0 = coop_gld(klines, r + 0, k_pad, key);
+  e0.c1 = coop_gld(klines, r + 1, k_pad, key);
+  evw.c0 = coop_gld(klines, r + 2, k_pad, key);
+  evw.c1 = coop_gld(klines, r + 3, k_pad, key);
+  evv.c0 = coop_gld(klines, r + 4, k_pad, key);
+  evv.c1 = coop_gld(klines, r + 5, k_pad, key);
+  fq2 l3, l4;
+  l3.c0 = fq_mul(evw.c0, h.y);
+  l3.c1 = fq_mul(evw.c1, h.y);
+  l4.c0 = fq_mul(evv.c0, h.x);
+  l4.c1 = fq_mul(evv.c1, h.x);
+  coop_emit_line(lines, 2 * (size_t)m, n_pad, item, e0, l3, l4);
+  fq2 b0 = fq2_one(), b3 = fq2_zero(), b4 = fq2_zero();
+  if (use_b) {
+    b0 = table[m].ell_0;
+    b3.c0 = fq_mul(table[m].ell_vw.c0, sy);
+    b3.c1 = fq_mul(table[m].ell_vw.c1, sy);
+    b4.c0 = fq_mul(table[m].ell_vv.c0, sx);
+    b4.c1 = fq_mul(table[m].ell_vv.c1, sx);
+  }
+  coop_emit_line(lines, 2 * (size_t)m + 1, n_pad, item, b0, b3, b4);
+}
+
 }  // namespace bn

@@ -270,6 +270,46 @@ def format_pairing_check_batch(msgs, msg_len, sigs, pks, compressed, ctx=None):
     return o.raw[:384 * n], st.raw[:n]
 
 
+class KeyLineCache:
+    """Cached line coefficients of a fixed key set (bn254_key_lines_prepare_dev): `verify(msgs, msg_len, sigs, key_index)` gives
+    verify_batch's statuses for triples (msg_i, sig_i, keys[key_index[i]]) without walking the keys again.  Device buffers are
+    torch CUDA tensors owned by this object (16 704 bytes per key)."""
+
+    def __init__(self, pks, ctx=None):
+        import torch
+        self.ctx = ctx or context()
+        self.n_keys = _n(pks, 128)
+        dev = torch.device("cuda", self.ctx.device)
+        self._torch = torch
+        nbytes = int(self.ctx.lib.bn254_key_lines_bytes(self.n_keys))
+        self.lines = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        self.status = torch.zeros(max(self.n_keys, 1), dtype=torch.uint8, device=dev)
+        d_pks = torch.frombuffer(bytearray(pks), dtype=torch.uint8).to(dev)
+        self.ctx.call("bn254_key_lines_prepare_dev", d_pks, S(self.n_keys), self.lines, self.status)
+        self.ctx.sync()
+
+    def key_status(self):
+        return bytes(self.status[:self.n_keys].cpu().numpy().tobytes())
+
+    def verify_dev(self, d_msgs, msg_len, d_sigs, n, d_status, d_key_index=None):
+        self.ctx.call("bn254_verify_batch_cached_dev", d_msgs, S(msg_len), d_sigs, self.lines, self.status, S(self.n_keys), d_key_index, S(n), d_status)
+
+    def verify(self, msgs, msg_len, sigs, key_index=None):
+        torch = self._torch
+        dev = self.lines.device
+        n = _n(sigs, 64)
+        _msgs_ok(msgs, msg_len, n)
+        up = lambda b: torch.frombuffer(bytearray(b if b else b"\0"), dtype=torch.uint8).to(dev)
+        d_idx = None
+        if key_index is not None:
+            import numpy as np
+            d_idx = torch.from_numpy(np.asarray(key_index, dtype=np.uint32).view(np.int32).copy()).to(dev)
+        st = torch.zeros(max(n, 1), dtype=torch.uint8, device=dev)
+        self.verify_dev(up(msgs), msg_len, up(sigs), n, st, d_idx)
+        self.ctx.sync()
+        return bytes(st[:n].cpu().numpy().tobytes())
+
+
 def layer_op_batch(op, data, n_in, n_out, ctx=None):
     ctx = ctx or context()
     n = _n(data, 32 * n_in)

@@ -118,6 +118,19 @@ int bn254_sign_batch_dev(bn254_ctx*, const uint8_t* msgs, size_t msg_len, const 
 int bn254_verify_batch(bn254_ctx*, const uint8_t* msgs, size_t msg_len, const uint8_t* sigs, const uint8_t* pks, size_t n, uint8_t* status);
 int bn254_verify_batch_dev(bn254_ctx*, const uint8_t* msgs, size_t msg_len, const uint8_t* sigs, const uint8_t* pks, size_t n, uint8_t* status);
 
+/* ECDSA::verify for keys that verify many messages (a fixed validator set) -- ADDITIONAL entry points with verify_batch's statuses.
+ * The walk of a key along the twist (the 87 line coefficient triples of the Miller loop) does not depend on the message:
+ * bn254_key_lines_prepare_dev does it once per key into a caller-owned device buffer of bn254_key_lines_bytes(n_keys) bytes
+ * (16 704 bytes per key, 16-byte aligned) and records each key's decode status under the context's input policy
+ * (key_status, n_keys bytes); bn254_verify_batch_cached_dev then verifies triple i against key key_index[i] (uint32, device;
+ * NULL = key i) and per item only scales the cached lines by H(msg_i) and the -G2 lines by sig_i.  status[i] = the key's decode
+ * status, the signature's, the hash's or the verdict, with the precedence of verify_batch; an index >= n_keys gives
+ * BN254_INDEX_OUT_OF_BOUNDS. */
+size_t bn254_key_lines_bytes(size_t n_keys);
+int bn254_key_lines_prepare_dev(bn254_ctx*, const uint8_t* pks, size_t n_keys, uint8_t* key_lines, uint8_t* key_status);
+int bn254_verify_batch_cached_dev(bn254_ctx*, const uint8_t* msgs, size_t msg_len, const uint8_t* sigs, const uint8_t* key_lines,
+                                  const uint8_t* key_status, size_t n_keys, const uint32_t* key_index, size_t n, uint8_t* status);
+
 /* Randomised batch form of ECDSA::verify -- an ADDITIONAL entry point, never used by verify_batch: the n
  * triples are accepted together iff  prod_i e(c_i H(msg_i), pk_i) * e(sum_i c_i sig_i, -G2) == 1  for 128-bit coefficients
  * c_i (coeffs16: n x 16 bytes, secret from whoever produced the signatures; NULL in the host-buffer form = drawn from

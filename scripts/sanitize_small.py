@@ -27,4 +27,30 @@ assert E.aggregate_verify_distinct(msgs, 32, pks, agg, ctx=ctx) == 0
 m = 5000
 h, st = E.hash_to_g1_batch(synth.messages(m, 32, seed=9), 32, m, ctx=ctx)
 assert not any(st)
+# round 2: the four-group block layout (more than two groups per SM), the untrusted policy's validation kernel (this context's
+# default), the cooperative pairing check, the formatter, and the device-resident aggregate checks with their cooperative finish
+import torch
+from bn254_b200 import dist as D
+big = 2 * 148 * 32 + 70
+bm, bk = synth.messages(big, 32, seed=13), synth.secret_keys(big, seed=14)
+bs, st = E.sign_batch(bm, 32, bk, ctx=ctx)
+bp = E.derive_pk_g2_batch(bk, ctx=ctx)
+assert E.verify_batch(bm, 32, bs, bp, ctx=ctx) == bytes(big)
+assert E.pairing_check_batch(sigs, pks, 1, n, ctx=ctx) == bytes([9]) * n
+neg_g2 = E.g2_sum(E.derive_pk_g2_batch((1).to_bytes(32, "big"), ctx=ctx), bytes([1]), ctx=ctx)[0]
+hs = E.hash_to_g1_batch(msgs, 32, n, ctx=ctx)[0]
+g1s = b"".join(hs[64 * i:64 * i + 64] + sigs[64 * i:64 * i + 64] for i in range(n))
+g2s = b"".join(pks[128 * i:128 * i + 128] + neg_g2 for i in range(n))
+assert E.pairing_check_batch(g1s, g2s, 2, n, ctx=ctx) == bytes(n)
+blob, st = E.format_pairing_check_batch(msgs, 32, sigs, pks, False, ctx=ctx)
+assert not any(st) and len(blob) == 384 * n
+dev = lambda b: torch.frombuffer(bytearray(b), dtype=torch.uint8).cuda()
+da = D.DistinctAggregate(ctx, world=1)
+da.step(dev(bm), 32, dev(bp), dev(bs), big)
+assert da.status() == 0
+E.set_input_policy(E.INPUTS_TYPED, ctx=ctx)
+sa = D.SameMessageAggregate(ctx, world=1)
+ms, st = E.sign_batch(b"m" * 70, 1, sks, ctx=ctx)
+sa.step(dev(b"m"), 1, dev(ms), dev(pks), n)
+assert sa.status() == 0
 print("sanitize_small ok")

@@ -970,3 +970,89 @@ def test_format_pairing_check_c_abi(E):
     with pytest.raises(Error) as e:
         format_pairing_check_uncompressed_values(b"m", sigs[:64] + b"x", pks[:128])
     assert e.value.variant == "SerializationError"
+
+
+def test_verify_with_cached_key_lines(E):
+    """A fixed key set (validators) verifying many messages: bn254_key_lines_prepare_dev walks every key once,
+    bn254_verify_batch_cached_dev only scales the cached lines per triple.  Statuses must be verify_batch's / the oracle's for
+    the same triples -- identity and permuted key indices, forged items, a bad key in the set, an index out of range, a
+    signature at infinity -- under both input policies."""
+    import edge_points
+    from bn254_b200._native import Context
+    nk = 300
+    sks = synth.secret_keys(nk, seed=901)
+    pks = bytearray(E.derive_pk_g2_batch(sks))
+    pks[128 * 7 + 127] ^= 1                                               # key 7 is not on the curve
+    pks[128 * 9:128 * 10] = bytes(128)                                    # key 9 is the point at infinity
+    pks = bytes(pks)
+    n = 5000
+    rng = random.Random(5)
+    idx = [rng.randrange(nk) for _ in range(n)]
+    idx[17] = nk + 3                                                      # out of range
+    msgs = synth.messages(n, 32, seed=902)
+    key_sk = lambda j: sks[32 * j:32 * j + 32]
+    sk_per_item = b"".join(key_sk(j if j < nk else 0) for j in idx)
+    sigs = bytearray(E.sign_batch(msgs, 32, sk_per_item)[0])
+    for i in (3, 1000, 4999):                                             # forged: signature of the neighbour
+        sigs[64 * i:64 * i + 64] = sigs[64 * (i - 1):64 * i]
+    sigs[64 * 40:64 * 41] = bytes(64)                                     # signature at infinity
+    sigs[64 * 41 + 10] ^= 4                                               # off-curve signature
+    sigs = bytes(sigs)
+    pk_per_item = b"".join(pks[128 * j:128 * j + 128] if j < nk else bytes(128) for j in idx)
+
+    cache = E.KeyLineCache(pks)                                           # module context: typed policy
+    ks = cache.key_status()
+    assert ks[7] == O.INVALID_GROUP_POINT and ks[9] == 0 and sum(1 for b in ks if b) == 1
+    got = cache.verify(msgs, 32, sigs, idx)
+    want = bytearray(E.verify_batch(msgs, 32, sigs, pk_per_item))
+    want[17] = O.INDEX_OOB
+    assert got == bytes(want)
+    bad = {i for i in range(n) if got[i]}
+    assert {3, 17, 40, 41, 1000, 4999} <= bad and all(idx[i] in (7, 9) or i in (3, 17, 40, 41, 1000, 4999) for i in bad)
+    sample = [i for i in range(0, n, 97)] + [3, 40, 41, 1000]
+    for i in sample:
+        if i != 17:
+            assert got[i] == O.verify(msgs[32 * i:32 * i + 32], sigs[64 * i:64 * i + 64], pk_per_item[128 * i:128 * i + 128]), i
+    # identity mapping (key_index == NULL): triple i against key i
+    m = nk
+    m_msgs = synth.messages(m, 32, seed=903)
+    m_sigs = E.sign_batch(m_msgs, 32, sks)[0]
+    assert cache.verify(m_msgs, 32, m_sigs) == E.verify_batch(m_msgs, 32, m_sigs, pks)
+    # more items than one workspace chunk, identity mapping (the second chunk's first item is key 4096, not key 0)
+    from bn254_b200._native import Context as _C
+    old = os.environ.get("BN254_COOP_CHUNK_LOG2")
+    os.environ["BN254_COOP_CHUNK_LOG2"] = "12"
+    try:
+        small = _C(0)
+    finally:
+        if old is None:
+            del os.environ["BN254_COOP_CHUNK_LOG2"]
+        else:
+            os.environ["BN254_COOP_CHUNK_LOG2"] = old
+    try:
+        E.set_input_policy(E.INPUTS_TYPED, ctx=small)
+        big = 9000
+        bm, bk = synth.messages(big, 32, seed=904), synth.secret_keys(big, seed=905)
+        bs = bytearray(E.sign_batch(bm, 32, bk)[0])
+        bs[64 * 8000:64 * 8001] = bs[64 * 1:64 * 2]
+        bp = E.derive_pk_g2_batch(bk)
+        c3 = E.KeyLineCache(bp, ctx=small)
+        st3 = c3.verify(bm, 32, bytes(bs))
+        assert st3 == E.verify_batch(bm, 32, bytes(bs), bp) and {i for i in range(big) if st3[i]} == {8000}
+    finally:
+        small.close()
+    # untrusted policy: the cache records from_uncompressed statuses (infinity and off-subgroup keys rejected), signatures validated
+    strict = Context(0)
+    try:
+        p2 = bytearray(pks)
+        p2[128 * 11:128 * 12] = edge_points.twist_point_outside_g2()
+        c2 = E.KeyLineCache(bytes(p2), ctx=strict)
+        ks2 = c2.key_status()
+        assert ks2[7] == ks2[9] == ks2[11] == O.INVALID_GROUP_POINT and sum(1 for b in ks2 if b) == 3
+        pk2_item = b"".join(bytes(p2)[128 * j:128 * j + 128] if j < nk else bytes(128) for j in idx)
+        want2 = bytearray(E.verify_batch(msgs, 32, sigs, pk2_item, ctx=strict))
+        want2[17] = O.INDEX_OOB
+        assert c2.verify(msgs, 32, sigs, idx) == bytes(want2)
+        assert want2[40] == O.INVALID_GROUP_POINT
+    finally:
+        strict.close()
