@@ -337,6 +337,27 @@ __global__ void __launch_bounds__(BN_BLOCK, BN_LINES_MINB) k_verify_lines(const 
   status[i] = (uint8_t)item_verify_lines(lines, n_pad, i, &h, sigs + 64 * i, pks + 128 * i, table, &consts[threadIdx.x]);
 }
 
+#ifndef BN_LINES_LAT_POLICY
+#define BN_LINES_LAT_POLICY lines_mul_ilp
+#endif
+// the same producer in its latency form (coop_lines.cuh lines_mul_ilp), one warp per block so that a small batch spreads over the SMs
+__global__ void __launch_bounds__(32) k_verify_lines_lat(const g1aff* __restrict__ H, const uint8_t* __restrict__ sigs, const uint8_t* __restrict__ pks,
+                                                         size_t n, u4* __restrict__ lines, size_t n_pad, uint8_t* __restrict__ status,
+                                                         const line_t* __restrict__ table) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (status[i]) return;
+  g1aff h;
+  if (H) {
+    h = H[i];
+  } else {
+    h.x = fq_from_limbs(K_G1_GEN_X);
+    h.y = fq_from_limbs(K_G1_GEN_Y);
+  }
+  __shared__ lines_consts consts[32];
+  status[i] = (uint8_t)item_verify_lines_t<BN_LINES_LAT_POLICY>(lines, n_pad, i, &h, sigs + 64 * i, pks + 128 * i, table, &consts[threadIdx.x]);
+}
+
 // Untrusted-input policy (the default, bn254_set_input_policy): sig / pk bytes are decoded exactly as
 // Signature::from_uncompressed / PublicKey::from_uncompressed would decode them (/root/reference/src/utils.rs:107-127):
 // field membership, curve equation -- which (0, 0), the engine's encoding of infinity, fails -- and for G2 the r-torsion
@@ -1110,6 +1131,7 @@ struct bn254_ctx {
   cudaMemPool_t pool = nullptr;  // private stream-ordered pool: every temporary of this context comes from it and goes back on destroy
   int input_policy = BN254_INPUTS_UNTRUSTED;
   int hash_try_limit = 255;      // /root/reference/src/hash.rs:39; lowered only by the test hook bn254_set_hash_try_limit
+  bool lines_throughput_only = false;  // BN254_LINES_LAT=0: never use the latency form of the line producer (measurement)
   std::string err;
   // optional per-phase timing of the verify pipeline (bn254_set_profiling): events recorded on `stream`
   bool prof = false;
@@ -1169,6 +1191,7 @@ int bn254_ctx_create(int device, bn254_ctx** out) {
     if (v >= 10 && v <= 21) ctx->chunk_log2 = v;
   }
   if (const char* w = getenv("BN254_COOP_H")) ctx->coop_h = w[0] == '1';
+  if (const char* w = getenv("BN254_LINES_LAT")) ctx->lines_throughput_only = w[0] == '0';
   if (const char* w = getenv("BN254_COOP_GROUPS4")) ctx->coop_groups4 = atoi(w);
   if (const char* w = getenv("BN254_COOP_STAGGER")) ctx->coop_stagger = (unsigned)atoi(w);  // tuning knob (cycles)
   auto fail = [&](const char* what, cudaError_t ee) {
@@ -1508,7 +1531,12 @@ static int verify_dev_impl(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, 
       LAUNCH(k_validate_inputs, grid_for(m), BN_BLOCK, sigs + 64 * off, pks + 128 * off, m, status + off);
     if (coop) {
       size_t m_pad = (m + COOP_LANES - 1) / COOP_LANES * COOP_LANES;
-      LAUNCH(k_verify_lines, grid_for(m), BN_BLOCK, h, sigs + 64 * off, pks + 128 * off, m, LN.as<u4>(), m_pad, status + off, ctx->d_lines);
+      // small batches: every warp is alone on its sub-partition and bound by the latency of its dependent carry chains -> the
+      // form with three products in flight (2.3 -> see profiles/r02_tuning_log.md section 4); big batches: the compact form
+      if (m <= (size_t)ctx->sm_count * 64 && !ctx->lines_throughput_only)
+        LAUNCH(k_verify_lines_lat, grid_for(m, 32), 32, h, sigs + 64 * off, pks + 128 * off, m, LN.as<u4>(), m_pad, status + off, ctx->d_lines);
+      else
+        LAUNCH(k_verify_lines, grid_for(m), BN_BLOCK, h, sigs + 64 * off, pks + 128 * off, m, LN.as<u4>(), m_pad, status + off, ctx->d_lines);
       CK(mark());
       if (wl)
         k_coopw_run<<<(unsigned)((m + COOPW_ITEMS - 1) / COOPW_ITEMS), COOPW_WARPS * 32, COOPW_SMEM_BYTES, ctx->stream>>>(

@@ -11,41 +11,125 @@
 
 namespace bn {
 
+// Fq2 product / square / scaling used by the walk, as a policy:
+//   lines_mul_call  the shared by-value routines of tower.cuh, one out-of-line Fq product each: smallest code and fewest live
+//                   registers -- the throughput form (big batches: every sub-partition has four warps to interleave);
+//   lines_mul_ilp   out-of-line Fq2 routines whose two or three Fq products are INLINED, so that their independent carry chains
+//                   interleave: 25 % slower per item when the SM is full (A/B r02), but a lone warp -- a small batch -- is bound by
+//                   the latency of its dependent chains, and three chains in flight hide it: the latency form.
+#if defined(__CUDACC__)
+#define BN_SFN static __device__ __forceinline__
+#else
+#define BN_SFN static inline
+#endif
+struct lines_mul_call {
+  BN_SFN fq2 mul(const fq2& a, const fq2& b) { return fq2_mul_v(a, b); }
+  BN_SFN fq2 sqr(const fq2& a) { return fq2_sqr_v(a); }
+  BN_SFN fq2 scale(const fq2& a, const fq& k) { return fq2_scale_v(a, k); }
+};
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__ fq2 fq2_mul_ilp(fq2 a, fq2 b) {
+  fq aa = fq_mul_inl(a.c0, b.c0);
+  fq bb = fq_mul_inl(a.c1, b.c1);
+  fq s = fq_mul_inl(fq_add(a.c0, a.c1), fq_add(b.c0, b.c1));
+  fq2 r;
+  r.c0 = fq_sub(aa, bb);
+  r.c1 = fq_sub(fq_sub(s, aa), bb);
+  return r;
+}
+__device__ __noinline__ fq2 fq2_sqr_ilp(fq2 a) {
+  fq m = fq_mul_inl(a.c0, a.c1);
+  fq2 r;
+  r.c0 = fq_mul_inl(fq_add(a.c0, a.c1), fq_sub(a.c0, a.c1));
+  r.c1 = fq_dbl(m);
+  return r;
+}
+__device__ __noinline__ fq2 fq2_scale_ilp(fq2 a, fq k) {
+  fq2 r;
+  r.c0 = fq_mul_inl(a.c0, k);
+  r.c1 = fq_mul_inl(a.c1, k);
+  return r;
+}
+struct lines_mul_ilp {
+  BN_SFN fq2 mul(const fq2& a, const fq2& b) { return fq2_mul_ilp(a, b); }
+  BN_SFN fq2 sqr(const fq2& a) { return fq2_sqr_ilp(a); }
+  BN_SFN fq2 scale(const fq2& a, const fq& k) { return fq2_scale_ilp(a, k); }
+};
+// everything inlined: the independent Fq2 products of a curve step (five in a doubling, up to four in an addition) can be
+// interleaved by the compiler as well -- 100+ KB of straight-line code per step, only sensible for a warp that is alone
+struct lines_mul_flat {
+  BN_SFN fq2 mul(const fq2& a, const fq2& b) {
+    fq aa = fq_mul_inl(a.c0, b.c0);
+    fq bb = fq_mul_inl(a.c1, b.c1);
+    fq s = fq_mul_inl(fq_add(a.c0, a.c1), fq_add(b.c0, b.c1));
+    fq2 r;
+    r.c0 = fq_sub(aa, bb);
+    r.c1 = fq_sub(fq_sub(s, aa), bb);
+    return r;
+  }
+  BN_SFN fq2 sqr(const fq2& a) {
+    fq m = fq_mul_inl(a.c0, a.c1);
+    fq2 r;
+    r.c0 = fq_mul_inl(fq_add(a.c0, a.c1), fq_sub(a.c0, a.c1));
+    r.c1 = fq_dbl(m);
+    return r;
+  }
+  BN_SFN fq2 scale(const fq2& a, const fq& k) {
+    fq2 r;
+    r.c0 = fq_mul_inl(a.c0, k);
+    r.c1 = fq_mul_inl(a.c1, k);
+    return r;
+  }
+};
+#else
+typedef lines_mul_call lines_mul_ilp;
+typedef lines_mul_call lines_mul_flat;
+#endif
+
 // the two curve steps of pairing.cuh with every Fq2 value passed in registers (same formulas, same results)
+template <class M>
 BN_FN void doubling_step_v(fq2& rx, fq2& ry, fq2& rz, fq2& ell_0, fq2& ell_vw, fq2& ell_vv) {
   const fq two_inv = fq_from_limbs(K_TWO_INV);
   const fq2 twist_b = fq2_from_limbs(K_TWIST_B);
-  fq2 a = fq2_scale_v(fq2_mul_v(rx, ry), two_inv);
-  fq2 b = fq2_sqr_v(ry);
-  fq2 cc = fq2_sqr_v(rz);
-  fq2 e = fq2_mul_v(twist_b, fq2_add(fq2_dbl(cc), cc));
+  fq2 a = M::scale(M::mul(rx, ry), two_inv);
+  fq2 b = M::sqr(ry);
+  fq2 cc = M::sqr(rz);
+  fq2 e = M::mul(twist_b, fq2_add(fq2_dbl(cc), cc));
   fq2 f = fq2_add(fq2_dbl(e), e);
-  fq2 g = fq2_scale_v(fq2_add(b, f), two_inv);
-  fq2 h = fq2_sub(fq2_sqr_v(fq2_add(ry, rz)), fq2_add(b, cc));
-  fq2 j = fq2_sqr_v(rx);
-  fq2 e2 = fq2_sqr_v(e);
-  rx = fq2_mul_v(a, fq2_sub(b, f));
-  ry = fq2_sub(fq2_sqr_v(g), fq2_add(fq2_dbl(e2), e2));
-  rz = fq2_mul_v(b, h);
+  fq2 g = M::scale(fq2_add(b, f), two_inv);
+  fq2 h = fq2_sub(M::sqr(fq2_add(ry, rz)), fq2_add(b, cc));
+  fq2 j = M::sqr(rx);
+  fq2 e2 = M::sqr(e);
+  rx = M::mul(a, fq2_sub(b, f));
+  ry = fq2_sub(M::sqr(g), fq2_add(fq2_dbl(e2), e2));
+  rz = M::mul(b, h);
   ell_0 = fq2_mul_xi(fq2_sub(e, b));
   ell_vw = fq2_neg(h);
   ell_vv = fq2_add(fq2_dbl(j), j);
 }
+template <class M>
 BN_FN void mixed_addition_step_v(const fq2& qx, const fq2& qy, fq2& rx, fq2& ry, fq2& rz, fq2& ell_0, fq2& ell_vw, fq2& ell_vv) {
-  fq2 d = fq2_sub(rx, fq2_mul_v(qx, rz));
-  fq2 e = fq2_sub(ry, fq2_mul_v(qy, rz));
-  fq2 f = fq2_sqr_v(d);
-  fq2 g = fq2_sqr_v(e);
-  fq2 h = fq2_mul_v(d, f);
-  fq2 i = fq2_mul_v(rx, f);
-  fq2 j = fq2_sub(fq2_add(h, fq2_mul_v(rz, g)), fq2_dbl(i));
-  fq2 t = fq2_mul_v(h, ry);
-  rx = fq2_mul_v(d, j);
-  ry = fq2_sub(fq2_mul_v(e, fq2_sub(i, j)), t);
-  rz = fq2_mul_v(rz, h);
-  ell_0 = fq2_mul_xi(fq2_sub(fq2_mul_v(e, qx), fq2_mul_v(d, qy)));
+  fq2 d = fq2_sub(rx, M::mul(qx, rz));
+  fq2 e = fq2_sub(ry, M::mul(qy, rz));
+  fq2 f = M::sqr(d);
+  fq2 g = M::sqr(e);
+  fq2 h = M::mul(d, f);
+  fq2 i = M::mul(rx, f);
+  fq2 j = fq2_sub(fq2_add(h, M::mul(rz, g)), fq2_dbl(i));
+  fq2 t = M::mul(h, ry);
+  rx = M::mul(d, j);
+  ry = fq2_sub(M::mul(e, fq2_sub(i, j)), t);
+  rz = M::mul(rz, h);
+  ell_0 = fq2_mul_xi(fq2_sub(M::mul(e, qx), M::mul(d, qy)));
   ell_vv = fq2_neg(e);
   ell_vw = d;
+}
+// (non-template names: the throughput form, used by every producer but the small-batch verify)
+BN_FN void doubling_step_v(fq2& rx, fq2& ry, fq2& rz, fq2& ell_0, fq2& ell_vw, fq2& ell_vv) {
+  doubling_step_v<lines_mul_call>(rx, ry, rz, ell_0, ell_vw, ell_vv);
+}
+BN_FN void mixed_addition_step_v(const fq2& qx, const fq2& qy, fq2& rx, fq2& ry, fq2& rz, fq2& ell_0, fq2& ell_vw, fq2& ell_vv) {
+  mixed_addition_step_v<lines_mul_call>(qx, qy, rx, ry, rz, ell_0, ell_vw, ell_vv);
 }
 
 // per-thread constants of the walk, kept in shared memory on the device (registers are for the running point):
@@ -71,8 +155,9 @@ BN_NOINLINE void coop_emit_scaled_v(u4* lines, size_t set, size_t n_pad, size_t 
 
 // returns the decode status of (sig, pk); on ST_OK all 174 line sets of the item are written.  K points at this thread's
 // constants block (shared memory on the device).
-BN_FN int item_verify_lines(u4* lines, size_t n_pad, size_t item, const g1aff* h, const uint8_t* sig, const uint8_t* pk, const line_t* table,
-                            lines_consts* K) {
+template <class M>
+BN_FN int item_verify_lines_t(u4* lines, size_t n_pad, size_t item, const g1aff* h, const uint8_t* sig, const uint8_t* pk, const line_t* table,
+                              lines_consts* K) {
   bool use_a, use_b;
   {
     g2j q;
@@ -95,13 +180,13 @@ BN_FN int item_verify_lines(u4* lines, size_t n_pad, size_t item, const g1aff* h
   size_t m = 0;
 #pragma unroll 1
   for (int k = 0; k < 64; k++) {
-    if (use_a) doubling_step_v(rx, ry, rz, c0, cvw, cvv);
+    if (use_a) doubling_step_v<M>(rx, ry, rz, c0, cvw, cvv);
     coop_emit_scaled_v(lines, 2 * m, n_pad, item, use_a, c0, cvw, cvv, K->v[2]);
     coop_emit_scaled_v(lines, 2 * m + 1, n_pad, item, use_b, table[m].ell_0, table[m].ell_vw, table[m].ell_vv, K->v[3]);
     m++;
     const int d = K_ATE_DIGITS[k];
     if (d != 0) {
-      if (use_a) mixed_addition_step_v(K->v[0], d > 0 ? K->v[1] : fq2_neg(K->v[1]), rx, ry, rz, c0, cvw, cvv);
+      if (use_a) mixed_addition_step_v<M>(K->v[0], d > 0 ? K->v[1] : fq2_neg(K->v[1]), rx, ry, rz, c0, cvw, cvv);
       coop_emit_scaled_v(lines, 2 * m, n_pad, item, use_a, c0, cvw, cvv, K->v[2]);
       coop_emit_scaled_v(lines, 2 * m + 1, n_pad, item, use_b, table[m].ell_0, table[m].ell_vw, table[m].ell_vv, K->v[3]);
       m++;
@@ -109,14 +194,18 @@ BN_FN int item_verify_lines(u4* lines, size_t n_pad, size_t item, const g1aff* h
   }
   fq2 q1x, q1y, q2x, q2y;
   g2_frobenius_pair(&q1x, &q1y, &q2x, &q2y, K->v[0], K->v[1]);
-  if (use_a) mixed_addition_step_v(q1x, q1y, rx, ry, rz, c0, cvw, cvv);
+  if (use_a) mixed_addition_step_v<M>(q1x, q1y, rx, ry, rz, c0, cvw, cvv);
   coop_emit_scaled_v(lines, 2 * m, n_pad, item, use_a, c0, cvw, cvv, K->v[2]);
   coop_emit_scaled_v(lines, 2 * m + 1, n_pad, item, use_b, table[m].ell_0, table[m].ell_vw, table[m].ell_vv, K->v[3]);
   m++;
-  if (use_a) mixed_addition_step_v(q2x, q2y, rx, ry, rz, c0, cvw, cvv);
+  if (use_a) mixed_addition_step_v<M>(q2x, q2y, rx, ry, rz, c0, cvw, cvv);
   coop_emit_scaled_v(lines, 2 * m, n_pad, item, use_a, c0, cvw, cvv, K->v[2]);
   coop_emit_scaled_v(lines, 2 * m + 1, n_pad, item, use_b, table[m].ell_0, table[m].ell_vw, table[m].ell_vv, K->v[3]);
   return ST_OK;
+}
+BN_FN int item_verify_lines(u4* lines, size_t n_pad, size_t item, const g1aff* h, const uint8_t* sig, const uint8_t* pk, const line_t* table,
+                            lines_consts* K) {
+  return item_verify_lines_t<lines_mul_call>(lines, n_pad, item, h, sig, pk, table, K);
 }
 
 // Multi-pairing producer: pair (h, pk) is stream `stream` of its lane `item`; its 87 line sets go to set index
