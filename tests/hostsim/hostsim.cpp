@@ -27,6 +27,14 @@ API int hs_hash_to_g1(const uint8_t* msg, size_t len, uint8_t* out, int* ctr) {
   fq_to_be(out, h.x); fq_to_be(out + 32, h.y);
   return 0;
 }
+// the same with the try limit of the device's test hook (bn254_set_hash_try_limit) and a first counter (the counter-parallel kernel)
+API int hs_hash_to_g1_limited(const uint8_t* msg, size_t len, uint8_t* out, int* ctr, int max_tries, int ctr_first) {
+  g1aff h;
+  int st = hash_to_g1(&h.x, &h.y, msg, len, ctr, max_tries, ctr_first);
+  if (st) { memset(out, 0, 64); return st; }
+  fq_to_be(out, h.x); fq_to_be(out + 32, h.y);
+  return 0;
+}
 API int hs_sign(const uint8_t* msg, size_t len, const uint8_t* sk, uint8_t* sig) {
   g1aff h;
   int st = hash_to_g1(&h.x, &h.y, msg, len, nullptr);

@@ -78,6 +78,28 @@ def test_hash_kats_and_random(hs):
         assert (st, out.raw, ctr.value) == (est, e, ectr)
 
 
+def test_hash_to_point_error_exit(hs):
+    """/root/reference/src/hash.rs:62: all counters fail -> HashToPointError.  Unreachable with 255 counters (2^-235), so the
+    device code takes the counter limit as a parameter (bn254_set_hash_try_limit): a message whose accepted counter is c must
+    fail with every limit <= c and succeed with c + 1, and a search that starts at counter c' > c must find the NEXT accepted
+    counter (what a lane of the counter-parallel kernel does)."""
+    rng = random.Random(31)
+    seen_fail = 0
+    for _ in range(60):
+        msg = rng.randbytes(rng.choice([5, 32, 60, 64, 100]))
+        est, e, c = O.hash_to_g1(msg)
+        assert est == 0
+        out, ctr = buf(64), ctypes.c_int(-1)
+        if c > 0:
+            assert hs.hs_hash_to_g1_limited(msg, len(msg), out, ctypes.byref(ctr), c, 0) == O.HASH_TO_POINT and out.raw == bytes(64)
+            seen_fail += 1
+        assert hs.hs_hash_to_g1_limited(msg, len(msg), out, ctypes.byref(ctr), c + 1, 0) == 0 and (out.raw, ctr.value) == (e, c)
+        assert hs.hs_hash_to_g1_limited(msg, len(msg), out, ctypes.byref(ctr), c + 1, c) == 0 and (out.raw, ctr.value) == (e, c)
+        st = hs.hs_hash_to_g1_limited(msg, len(msg), out, ctypes.byref(ctr), 255, c + 1)
+        assert st == 0 and ctr.value > c and out.raw != e
+    assert seen_fail > 20
+
+
 def test_sign_kat_and_group_vectors(hs):
     for v in G["sign"]:
         sig = buf(64)
