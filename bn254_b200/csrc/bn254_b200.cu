@@ -343,10 +343,13 @@ __global__ void __launch_bounds__(BN_BLOCK, BN_LINES_MINB) k_verify_lines(const 
 // the same producer in its latency form (coop_lines.cuh lines_mul_ilp), one warp per block so that a small batch spreads over the SMs
 __global__ void __launch_bounds__(32) k_verify_lines_lat(const g1aff* __restrict__ H, const uint8_t* __restrict__ sigs, const uint8_t* __restrict__ pks,
                                                          size_t n, u4* __restrict__ lines, size_t n_pad, uint8_t* __restrict__ status,
-                                                         const line_t* __restrict__ table) {
+                                                         const line_t* __restrict__ table, unsigned* __restrict__ progress) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  if (status[i]) return;
+  if (status[i]) {
+    if (progress) *((volatile unsigned*)progress + i) = 0xffffffffu;  // nothing will be written: do not keep the machine waiting
+    return;
+  }
   g1aff h;
   if (H) {
     h = H[i];
@@ -355,7 +358,14 @@ __global__ void __launch_bounds__(32) k_verify_lines_lat(const g1aff* __restrict
     h.y = fq_from_limbs(K_G1_GEN_Y);
   }
   __shared__ lines_consts consts[32];
-  status[i] = (uint8_t)item_verify_lines_t<BN_LINES_LAT_POLICY>(lines, n_pad, i, &h, sigs + 64 * i, pks + 128 * i, table, &consts[threadIdx.x]);
+  const int st = item_verify_lines_t<BN_LINES_LAT_POLICY>(lines, n_pad, i, &h, sigs + 64 * i, pks + 128 * i, table, &consts[threadIdx.x],
+                                                          progress ? progress + i : nullptr);
+  // (pipelined: the machine may already be past its own status check, so the status is final before the release below)
+  status[i] = (uint8_t)st;
+  if (progress) {
+    __threadfence();
+    *((volatile unsigned*)progress + i) = 0xffffffffu;
+  }
 }
 
 // Untrusted-input policy (the default, bn254_set_input_policy): sig / pk bytes are decoded exactly as
@@ -398,7 +408,8 @@ __global__ void __launch_bounds__(BN_BLOCK) k_validate_inputs(const uint8_t* __r
 // 3 final exponentiation of fio (+ verdict), 4 multi-pairing: COOP_MULTI_K pairs per lane, block product -> fio
 __global__ void __launch_bounds__(COOP_THREADS, BN_COOP_MINB) k_coop_run(int which, size_t n, size_t n_pad, const u4* __restrict__ lines,
                                                                          u4* __restrict__ gslots, u4* __restrict__ fio,
-                                                                         uint8_t* __restrict__ status, unsigned stagger, unsigned sms) {
+                                                                         uint8_t* __restrict__ status, unsigned stagger, unsigned sms,
+                                                                         const unsigned* progress) {
   extern __shared__ u4 coop_sm[];
   // Blocks that share an SM run the same program at the same speed: started together they stay in lockstep, so their
   // multiply-free stretches (commit, barriers) coincide and the multiplier pipe idles for all of them at once.  The k-th
@@ -427,6 +438,10 @@ __global__ void __launch_bounds__(COOP_THREADS, BN_COOP_MINB) k_coop_run(int whi
   c.gslots = gslots;
   c.fio = fio;
   c.status = status;
+  c.progress = nullptr;
+  c.sets_per_step = 1;
+  c.progress = progress;
+  c.sets_per_step = 2;  // (only the verify program is ever run pipelined)
   coop_run_block(c, coop_program(which), [] { COOP_BARRIER(); });
 }
 
@@ -465,6 +480,8 @@ __global__ void __launch_bounds__(COOP4_THREADS, 1) k_coop4_run(int which, size_
   c.gslots = gslots;
   c.fio = fio;
   c.status = status;
+  c.progress = nullptr;
+  c.sets_per_step = 1;
   const int bar = g + 1;
   coop_run_block(c, coop_program(which), [bar] { asm volatile("bar.sync %0, %1;" ::"r"(bar), "n"(COOP_THREADS) : "memory"); });
 }
@@ -500,6 +517,8 @@ __global__ void __launch_bounds__(COOP4_THREADS, 1) k_cooph_run(int which, size_
   c.gslots = gslots;
   c.fio = fio;
   c.status = status;
+  c.progress = nullptr;
+  c.sets_per_step = 1;
   const uint32_t* prog = coop_program(which);
   // the second group of every sub-partition starts late, so that the two do not run their phases in step
   if (offset_cycles && g >= 4) {
@@ -554,6 +573,8 @@ __global__ void __launch_bounds__(COOPW_WARPS * 32, BN_COOP_MINB) k_coopw_run(in
   c.gslots = gslots;
   c.fio = fio;
   c.status = status;
+  c.progress = nullptr;
+  c.sets_per_step = 1;
   const uint32_t* prog = coop_program(which);
   int line_next = 0;
 #pragma unroll 1
@@ -1115,6 +1136,9 @@ struct bn254_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // host-buffer verify: signatures and keys are uploaded here while the hash kernels run
   cudaEvent_t ev_alloc = nullptr, ev_copy = nullptr;
+  cudaStream_t aux_stream = nullptr;   // small-batch verify: the line producer runs here WHILE the machine consumes its line sets
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool pipeline_small = true;          // BN254_PIPELINE=0 turns the producer / machine overlap off (measurement)
   line_t* d_lines = nullptr;
   aff<fq>* d_comb_g1 = nullptr;   // (d + 1) * 16^w * G1 generator
   aff<fq2>* d_comb_g2 = nullptr;  // (d + 1) * 16^w * G2 generator
@@ -1210,6 +1234,10 @@ int bn254_ctx_create(int device, bn254_ctx** out) {
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
   if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate(copy)", e);
   if ((e = cudaEventCreateWithFlags(&ctx->ev_alloc, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+  if ((e = cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate(aux)", e);
+  if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+  if ((e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+  if (const char* w = getenv("BN254_PIPELINE")) ctx->pipeline_small = w[0] != '0';
   if ((e = cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
   // A private pool (the device's default pool is shared with the host process, e.g. torch): freed blocks stay cached here
   // between calls -- the line-set workspace of verify is allocated once, not per call -- and everything is returned to the
@@ -1257,6 +1285,12 @@ void bn254_ctx_destroy(bn254_ctx* ctx) {
     cudaStreamSynchronize(ctx->copy_stream);
     cudaStreamDestroy(ctx->copy_stream);
   }
+  if (ctx->aux_stream) {
+    cudaStreamSynchronize(ctx->aux_stream);
+    cudaStreamDestroy(ctx->aux_stream);
+  }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->ev_alloc) cudaEventDestroy(ctx->ev_alloc);
   if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1441,13 +1475,13 @@ int bn254_sign_batch(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, const 
 // one launch of the block-layout cooperative machine over `groups` 32-item groups: four groups per 24-warp block (one per
 // sub-partition, k_coop4_run) unless the context asks for the one-group-per-block kernel (pairing mode 2)
 static int launch_coop_groups(bn254_ctx* ctx, int which, size_t n, size_t n_pad, const u4* lines, u4* gslots, u4* fio, uint8_t* status,
-                              size_t groups) {
+                              size_t groups, const unsigned* progress = nullptr) {
   const size_t sms = (size_t)ctx->sm_count;
   auto one_group_blocks = [&](size_t g0, size_t cnt) {  // groups g0 .. g0 + cnt - 1, one six-warp block each
     const size_t i0 = g0 * COOP_LANES;
     k_coop_run<<<(unsigned)cnt, COOP_THREADS, COOP1_SMEM_BYTES, ctx->stream>>>(which, n > i0 ? n - i0 : 0, n_pad, lines + i0, gslots ? gslots + i0 : gslots,
                                                                             fio ? fio + i0 : fio, status ? status + i0 : status, ctx->coop_stagger,
-                                                                            (unsigned)sms);
+                                                                            (unsigned)sms, progress ? progress + i0 : progress);
     ctx->launches++;
   };
   if (ctx->pairing_mode == 2 || !ctx->coop_groups4) {
@@ -1532,9 +1566,35 @@ static int verify_dev_impl(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, 
     if (coop) {
       size_t m_pad = (m + COOP_LANES - 1) / COOP_LANES * COOP_LANES;
       // small batches: every warp is alone on its sub-partition and bound by the latency of its dependent carry chains -> the
-      // form with three products in flight (2.3 -> see profiles/r02_tuning_log.md section 4); big batches: the compact form
-      if (m <= (size_t)ctx->sm_count * 64 && !ctx->lines_throughput_only)
-        LAUNCH(k_verify_lines_lat, grid_for(m, 32), 32, h, sigs + 64 * off, pks + 128 * off, m, LN.as<u4>(), m_pad, status + off, ctx->d_lines);
+      // form with three products in flight (profiles/r02_tuning_log.md section 4); big batches: the compact form
+      const bool lat = m <= (size_t)ctx->sm_count * 64 && !ctx->lines_throughput_only;
+      // At most one group per SM, default layout: producer and machine run CONCURRENTLY.  The producer (aux stream) publishes,
+      // per item, how many Miller steps' line sets are in memory; the machine waits for a step's count before it fetches the
+      // step's sets, so its Miller loop hides under the walk and only the final exponentiation is left after it.  Both grids
+      // fit the GPU together (<= 148 one-warp blocks + <= 148 six-warp blocks), so neither can starve the other.
+      const bool piped = lat && !wl && !hl && ctx->pairing_mode == 0 && ctx->coop_groups4 && ctx->pipeline_small && !ctx->prof && n <= CHUNK &&
+                         m_pad / COOP_LANES <= (size_t)ctx->sm_count;
+      if (piped) {
+        DALLOC(PR, sizeof(unsigned) * m_pad);
+        CK(cudaMemsetAsync(PR.p, 0, sizeof(unsigned) * m_pad, ctx->stream));
+        CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+        k_verify_lines_lat<<<grid_for(m, 32), 32, 0, ctx->aux_stream>>>(h, sigs + 64 * off, pks + 128 * off, m, LN.as<u4>(), m_pad, status + off,
+                                                                        ctx->d_lines, PR.as<unsigned>());
+        ctx->launches++;
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
+        int rc = launch_coop_groups(ctx, 0, m, m_pad, LN.as<u4>(), GS.as<u4>(), (u4*)nullptr, status + off, m_pad / COOP_LANES, PR.as<unsigned>());
+        if (rc) {
+          cudaStreamSynchronize(ctx->aux_stream);
+          return rc;
+        }
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));  // everything after this call (frees included) is ordered after the producer
+        continue;
+      }
+      if (lat)
+        LAUNCH(k_verify_lines_lat, grid_for(m, 32), 32, h, sigs + 64 * off, pks + 128 * off, m, LN.as<u4>(), m_pad, status + off, ctx->d_lines,
+               (unsigned*)nullptr);
       else
         LAUNCH(k_verify_lines, grid_for(m), BN_BLOCK, h, sigs + 64 * off, pks + 128 * off, m, LN.as<u4>(), m_pad, status + off, ctx->d_lines);
       CK(mark());
@@ -2289,7 +2349,7 @@ static int finish_payloads_dev(bn254_ctx* ctx, const uint8_t* payloads, size_t m
   DALLOC(GSf, sizeof(u4) * COOP_GSLOTS * 6 * 2 * 2 * COOP_LANES);
   LAUNCH(k_finish_prepare, 1, BN_BLOCK, payloads, (int)m, agg_sig, ctx->d_lines, LNf.as<u4>(), FIOf.as<u4>(), status);
   k_coop_run<<<1, COOP_THREADS, COOP1_SMEM_BYTES, ctx->stream>>>(CPROG_FINISH, (size_t)1, (size_t)COOP_LANES, LNf.as<u4>(), GSf.as<u4>(), FIOf.as<u4>(), status,
-                                                                0u, (unsigned)ctx->sm_count);
+                                                                0u, (unsigned)ctx->sm_count, (const unsigned*)nullptr);
   ctx->launches++;
   CK(cudaGetLastError());
   return 0;

@@ -155,9 +155,21 @@ BN_NOINLINE void coop_emit_scaled_v(u4* lines, size_t set, size_t n_pad, size_t 
 
 // returns the decode status of (sig, pk); on ST_OK all 174 line sets of the item are written.  K points at this thread's
 // constants block (shared memory on the device).
+// publish "the line sets of the first `steps` Miller steps of this item are in memory" to a consumer that runs concurrently
+BN_FN void lines_publish(unsigned* progress, unsigned steps) {
+#if defined(__CUDA_ARCH__)
+  if (progress) {
+    __threadfence();
+    *(volatile unsigned*)progress = steps;
+  }
+#else
+  (void)progress;
+  (void)steps;
+#endif
+}
 template <class M>
 BN_FN int item_verify_lines_t(u4* lines, size_t n_pad, size_t item, const g1aff* h, const uint8_t* sig, const uint8_t* pk, const line_t* table,
-                              lines_consts* K) {
+                              lines_consts* K, unsigned* progress = nullptr) {
   bool use_a, use_b;
   {
     g2j q;
@@ -184,12 +196,14 @@ BN_FN int item_verify_lines_t(u4* lines, size_t n_pad, size_t item, const g1aff*
     coop_emit_scaled_v(lines, 2 * m, n_pad, item, use_a, c0, cvw, cvv, K->v[2]);
     coop_emit_scaled_v(lines, 2 * m + 1, n_pad, item, use_b, table[m].ell_0, table[m].ell_vw, table[m].ell_vv, K->v[3]);
     m++;
+    lines_publish(progress, (unsigned)m);
     const int d = K_ATE_DIGITS[k];
     if (d != 0) {
       if (use_a) mixed_addition_step_v<M>(K->v[0], d > 0 ? K->v[1] : fq2_neg(K->v[1]), rx, ry, rz, c0, cvw, cvv);
       coop_emit_scaled_v(lines, 2 * m, n_pad, item, use_a, c0, cvw, cvv, K->v[2]);
       coop_emit_scaled_v(lines, 2 * m + 1, n_pad, item, use_b, table[m].ell_0, table[m].ell_vw, table[m].ell_vv, K->v[3]);
       m++;
+      lines_publish(progress, (unsigned)m);
     }
   }
   fq2 q1x, q1y, q2x, q2y;
@@ -198,6 +212,7 @@ BN_FN int item_verify_lines_t(u4* lines, size_t n_pad, size_t item, const g1aff*
   coop_emit_scaled_v(lines, 2 * m, n_pad, item, use_a, c0, cvw, cvv, K->v[2]);
   coop_emit_scaled_v(lines, 2 * m + 1, n_pad, item, use_b, table[m].ell_0, table[m].ell_vw, table[m].ell_vv, K->v[3]);
   m++;
+  lines_publish(progress, (unsigned)m);
   if (use_a) mixed_addition_step_v<M>(q2x, q2y, rx, ry, rz, c0, cvw, cvv);
   coop_emit_scaled_v(lines, 2 * m, n_pad, item, use_a, c0, cvw, cvv, K->v[2]);
   coop_emit_scaled_v(lines, 2 * m + 1, n_pad, item, use_b, table[m].ell_0, table[m].ell_vw, table[m].ell_vv, K->v[3]);

@@ -245,7 +245,7 @@ struct coop_sim {
     c.sm = sm.data() + lane; c.row = row; c.wmode = wmode; c.plans = g_coop_wmode == 1 ? K_COOP_PLANS_W : g_coop_wmode == 2 ? K_COOP_PLANS_H : K_COOP_PLANS;
     c.kq = g_coop_wmode == 0 ? &K_KQ_TABLE[0][0] : nullptr;  // the default kernel's one-reduction xi variants; the other layouts keep the additions
     c.k = k; c.lane = lane; c.active = true; c.item = lane; c.n_pad = n_pad;
-    c.lines = lines.data(); c.gslots = gslots.data(); c.fio = fio.data(); c.status = &status;
+    c.lines = lines.data(); c.gslots = gslots.data(); c.fio = fio.data(); c.status = &status; c.progress = nullptr; c.sets_per_step = 1;
     return c;
   }
   void run(const uint32_t* prog) {

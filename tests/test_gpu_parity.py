@@ -1056,3 +1056,47 @@ def test_verify_with_cached_key_lines(E):
         assert want2[40] == O.INVALID_GROUP_POINT
     finally:
         strict.close()
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 33, 148 * 32, 148 * 32 + 1])
+def test_small_batch_latency_path(E, n):
+    """Small batches take the low-latency route (counter-parallel hash, the latency form of the line producer on its own stream,
+    one-group blocks of the machine consuming the line sets WHILE they are produced): verdicts must be the oracle's, with forged,
+    undecodable and infinite items in the batch, under both input policies, and equal to the unpipelined route (BN254_PIPELINE=0).
+    148 * 32 is the last batch that is pipelined, 148 * 32 + 1 the first that is not."""
+    from bn254_b200._native import Context
+    msgs, sks, sigs, pks = _signed_set(E, n, seed=1000 + n)
+    msgs, sigs, pks = bytearray(msgs), bytearray(sigs), bytearray(pks)
+    rng = random.Random(n)
+    marks = {}
+    for i in rng.sample(range(n), min(n, 7)):
+        kind = rng.randrange(5) if n > 1 else 0
+        marks[i] = kind
+        if kind == 0:
+            msgs[32 * i + 3] ^= 0x10                                  # wrong message
+        elif kind == 1:
+            j = (i + 1) % n
+            sigs[64 * i:64 * i + 64] = sigs[64 * j:64 * j + 64] if j != i else O.g1_neg(bytes(sigs[64 * i:64 * i + 64]))[1]
+        elif kind == 2:
+            sigs[64 * i + 63] ^= 1                                    # off-curve signature: decode error, no line sets written
+        elif kind == 3:
+            sigs[64 * i:64 * i + 64] = bytes(64)                      # infinity (typed: skipped pair -> reject; untrusted: decode error)
+        else:
+            pks[128 * i:128 * i + 32] = be(Q + 2)                     # coordinate >= q
+    msgs, sigs, pks = bytes(msgs), bytes(sigs), bytes(pks)
+    want = O.verify_batch(msgs, 32, sigs, pks, n, NTHREADS)
+    assert E.verify_batch(msgs, 32, sigs, pks) == want
+    strict = Context(0)
+    os.environ["BN254_PIPELINE"] = "0"
+    try:
+        plain = Context(0)
+    finally:
+        del os.environ["BN254_PIPELINE"]
+    try:
+        E.set_input_policy(E.INPUTS_TYPED, ctx=plain)
+        assert E.verify_batch(msgs, 32, sigs, pks, ctx=plain) == want
+        want_strict = bytes(_untrusted_expect(msgs[32 * i:32 * i + 32], sigs[64 * i:64 * i + 64], pks[128 * i:128 * i + 128]) for i in range(min(n, 64)))
+        assert E.verify_batch(msgs, 32, sigs, pks, ctx=strict)[:len(want_strict)] == want_strict
+    finally:
+        strict.close()
+        plain.close()
