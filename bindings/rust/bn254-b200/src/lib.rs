@@ -63,6 +63,7 @@ fn status_to_result(code: u8) -> Result<()> {
         8 => Err(Error::PointInJacobian),
         9 => Err(Error::VerificationFailed),
         10 => Err(Error::SerializationError),
+        255 => Err(Error::Engine("item not evaluated (BN254_ENGINE_FAULT): retry the call".into())),
         other => Err(Error::Engine(format!("unknown status byte {other}"))),
     }
 }

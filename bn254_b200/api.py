@@ -19,6 +19,7 @@ ERROR_NAMES = {
     1: "HashToPointError", 2: "IndexOutOfBounds", 3: "InvalidEncoding", 4: "InvalidGroupPoint", 5: "InvalidLength",
     6: "NotMemberError", 7: "ToAffineConversion", 8: "PointInJacobian", 9: "VerificationFailed", 10: "SerializationError",
     11: "HexDecodeFailed",
+    255: "EngineFault",  # not a variant of the crate: the engine did not evaluate the item (include/bn254_b200.h BN254_ENGINE_FAULT)
 }
 
 

@@ -360,12 +360,65 @@ __global__ void __launch_bounds__(32) k_verify_lines_lat(const g1aff* __restrict
   __shared__ lines_consts consts[32];
   const int st = item_verify_lines_t<BN_LINES_LAT_POLICY>(lines, n_pad, i, &h, sigs + 64 * i, pks + 128 * i, table, &consts[threadIdx.x],
                                                           progress ? progress + i : nullptr);
-  // (pipelined: the machine may already be past its own status check, so the status is final before the release below)
-  status[i] = (uint8_t)st;
+  // (pipelined: the machine may already be past its own status check, so the status is final before the release below;
+  // a zero is never written: the machine may have reported a fault for this item in the meantime)
+  if (st) status[i] = (uint8_t)st;
   if (progress) {
     __threadfence();
     *((volatile unsigned*)progress + i) = 0xffffffffu;
   }
+}
+
+// the producer of small batches: four warps walk the 32 items of a group together (coop_lines.cuh "cooperative walk"), one block per group
+__global__ void __launch_bounds__(WALK_WARPS * 32, 4) k_verify_lines_walk4(const g1aff* __restrict__ H, const uint8_t* __restrict__ sigs,
+                                                                        const uint8_t* __restrict__ pks, size_t n, u4* __restrict__ lines, size_t n_pad,
+                                                                        uint8_t* __restrict__ status, const line_t* __restrict__ table,
+                                                                        unsigned* __restrict__ progress) {
+  extern __shared__ u4 walk_sm[];
+  walk_ctx c;
+  c.lane = threadIdx.x & 31;
+  c.warp = threadIdx.x >> 5;
+  c.sm = walk_sm + c.lane;
+  c.flags = (int*)(walk_sm + WS_SLOTS * 2 * 2 * COOP_LANES);
+  c.row = COOP_LANES;
+  c.item = (size_t)blockIdx.x * COOP_LANES + c.lane;
+  c.n = n;
+  c.n_pad = n_pad;
+  c.lines = lines;
+  c.table = table;
+  const bool skip = c.item >= n || status[c.item] != 0;  // (an item that already failed: nothing is read, nothing is written)
+  g1aff h;
+  if (!skip && H) {
+    h = H[c.item];
+  } else {
+    h.x = fq_from_limbs(K_G1_GEN_X);
+    h.y = fq_from_limbs(K_G1_GEN_Y);
+  }
+  walk_decode(c, &h, sigs + 64 * c.item, pks + 128 * c.item, skip);
+  __syncthreads();
+  const int st = walk_flags(c, skip);
+  const bool reporter = c.warp == WALK_WARPS - 1 && c.item < n;  // the warp with the shortest first level reports for the group
+  if (reporter && !c.live) {  // no line set will be written: the status is final, do not keep a pipelined machine waiting
+    if (!skip) status[c.item] = (uint8_t)st;
+    if (progress) {
+      __threadfence();
+      *((volatile unsigned*)progress + c.item) = 0xffffffffu;
+    }
+  }
+  walk_schedule(
+      [&](int kind, int level, size_t m, int sqx, int sqy) {
+        if (kind == 0)
+          walk_dbl<lines_mul_ilp>(c, level, m);
+        else
+          walk_add<lines_mul_ilp>(c, level, m, sqx, sqy);
+      },
+      [] { __syncthreads(); },
+      [&](size_t m) {  // every store of steps < m is before the barrier this thread has just left: fence, then publish
+        if (progress && reporter && c.live) {
+          __threadfence();
+          *((volatile unsigned*)progress + c.item) = m < K_N_LINES ? (unsigned)m : 0xffffffffu;
+        }
+      });
 }
 
 // Untrusted-input policy (the default, bn254_set_input_policy): sig / pk bytes are decoded exactly as
@@ -443,6 +496,44 @@ __global__ void __launch_bounds__(COOP_THREADS, BN_COOP_MINB) k_coop_run(int whi
   c.progress = progress;
   c.sets_per_step = 2;  // (only the verify program is ever run pipelined)
   coop_run_block(c, coop_program(which), [] { COOP_BARRIER(); });
+}
+
+// ---- latency layout (coop.cuh coop_run_block12): one 32-item group per TWELVE-warp block, for launches of at most one group per SM
+#define COOP12_THREADS (2 * COOP_THREADS)
+// group slots + six exchange slots + the k q table = 61 792 bytes, REQUESTED as 66 KB: a block of this kernel fills an SM's register
+// file to 3/4, so the driver would pick the smallest shared-memory carve-out that holds one block (64 KB) and leave 1 KB over --
+// and a pipelined producer block (10 KB) dispatched behind the machine could then never become resident next to it while the
+// machine waits for its line sets.  66 KB forces the 100 KB carve-out (or larger) on every configuration the SM has.
+#define COOP12_SMEM_USED (COOP_SMEM_BYTES + 6 * 2 * COOP_LANES * 16 + 11 * 32)
+#define COOP12_SMEM_BYTES (66 * 1024)
+static_assert(COOP12_SMEM_USED <= COOP12_SMEM_BYTES, "latency layout: shared memory");
+__global__ void __launch_bounds__(COOP12_THREADS, 1) k_coop12_run(int which, size_t n, size_t n_pad, const u4* __restrict__ lines,
+                                                                  u4* __restrict__ gslots, u4* __restrict__ fio, uint8_t* __restrict__ status,
+                                                                  const unsigned* progress) {
+  extern __shared__ u4 coop_sm[];
+  u4* xch_base = coop_sm + COOP_SLOTS * 2 * COOP_LANES;
+  uint32_t* kq = (uint32_t*)(xch_base + 6 * 2 * COOP_LANES);
+  if (threadIdx.x < 88) kq[threadIdx.x] = (&K_KQ_TABLE[0][0])[threadIdx.x];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5;
+  coop_ctx c;
+  c.k = warp % COOP_WARPS;
+  c.lane = threadIdx.x & 31;
+  c.sm = coop_sm + c.lane;
+  c.row = COOP_LANES;
+  c.wmode = false;
+  c.plans = K_COOP_PLANS;
+  c.kq = kq;
+  c.item = (size_t)blockIdx.x * COOP_LANES + c.lane;
+  c.active = c.item < n;
+  c.n_pad = n_pad;
+  c.lines = lines;
+  c.gslots = gslots;
+  c.fio = fio;
+  c.status = status;
+  c.progress = progress;
+  c.sets_per_step = 2;
+  coop_run_block12(c, warp / COOP_WARPS, xch_base + c.lane, coop_program(which), [] { __syncthreads(); });
 }
 
 // ---- the same block-layout machine with FOUR 32-item groups in one 24-warp block (one block per SM).  Warp w of a block
@@ -1139,6 +1230,9 @@ struct bn254_ctx {
   cudaStream_t aux_stream = nullptr;   // small-batch verify: the line producer runs here WHILE the machine consumes its line sets
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool pipeline_small = true;          // BN254_PIPELINE=0 turns the producer / machine overlap off (measurement)
+  bool lines_walk4 = true;             // BN254_LINES_WALK4=0: small batches use the one-thread-per-item latency producer (measurement)
+  int coop12_piped_max = 1 << 30;      // BN254_COOP12_PIPED_MAX: most groups of a PIPELINED launch that still get twelve-warp blocks
+  bool coop12 = true;                  // BN254_COOP12=0: six-warp blocks even when a group has an SM to itself (measurement)
   line_t* d_lines = nullptr;
   aff<fq>* d_comb_g1 = nullptr;   // (d + 1) * 16^w * G1 generator
   aff<fq2>* d_comb_g2 = nullptr;  // (d + 1) * 16^w * G2 generator
@@ -1238,6 +1332,9 @@ int bn254_ctx_create(int device, bn254_ctx** out) {
   if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
   if ((e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
   if (const char* w = getenv("BN254_PIPELINE")) ctx->pipeline_small = w[0] != '0';
+  if (const char* w = getenv("BN254_COOP12")) ctx->coop12 = w[0] != '0';
+  if (const char* w = getenv("BN254_COOP12_PIPED_MAX")) ctx->coop12_piped_max = atoi(w);
+  if (const char* w = getenv("BN254_LINES_WALK4")) ctx->lines_walk4 = w[0] != '0';
   if ((e = cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
   // A private pool (the device's default pool is shared with the host process, e.g. torch): freed blocks stay cached here
   // between calls -- the line-set workspace of verify is allocated once, not per call -- and everything is returned to the
@@ -1262,6 +1359,15 @@ int bn254_ctx_create(int device, bn254_ctx** out) {
   ctx->launches++;
   if ((e = cudaGetLastError()) != cudaSuccess) return fail("k_init_comb launch", e);
   if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return fail("k_init_lines / k_init_comb", e);
+  if ((e = cudaFuncSetAttribute(k_coop12_run, cudaFuncAttributeMaxDynamicSharedMemorySize, COOP12_SMEM_BYTES)) != cudaSuccess)
+    return fail("cudaFuncSetAttribute(k_coop12_run)", e);
+  // the pipelined pair (producer + machine) must be co-resident on every SM whichever of the two is dispatched first
+  cudaFuncSetAttribute(k_coop12_run, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(k_coop_run, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(k_verify_lines_lat, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if ((e = cudaFuncSetAttribute(k_verify_lines_walk4, cudaFuncAttributeMaxDynamicSharedMemorySize, WALK_SMEM_BYTES)) != cudaSuccess)
+    return fail("cudaFuncSetAttribute(k_verify_lines_walk4)", e);
+  cudaFuncSetAttribute(k_verify_lines_walk4, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if ((e = cudaFuncSetAttribute(k_coop_run, cudaFuncAttributeMaxDynamicSharedMemorySize, COOP1_SMEM_BYTES)) != cudaSuccess)
     return fail("cudaFuncSetAttribute(k_coop_run)", e);
   if ((e = cudaFuncSetAttribute(k_coopw_run, cudaFuncAttributeMaxDynamicSharedMemorySize, COOPW_SMEM_BYTES)) != cudaSuccess)
@@ -1477,8 +1583,18 @@ int bn254_sign_batch(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, const 
 static int launch_coop_groups(bn254_ctx* ctx, int which, size_t n, size_t n_pad, const u4* lines, u4* gslots, u4* fio, uint8_t* status,
                               size_t groups, const unsigned* progress = nullptr) {
   const size_t sms = (size_t)ctx->sm_count;
-  auto one_group_blocks = [&](size_t g0, size_t cnt) {  // groups g0 .. g0 + cnt - 1, one six-warp block each
+  auto one_group_blocks = [&](size_t g0, size_t cnt) {  // groups g0 .. g0 + cnt - 1, one block each
     const size_t i0 = g0 * COOP_LANES;
+    // a group has an SM to itself: twelve warps per group (latency layout).  Pipelined, only up to half the SMs: a twelve-warp
+    // block leaves 4096 registers per sub-partition, a producer warp needs up to 8192 -- producer blocks cannot become resident
+    // NEXT to such a block, they need SMs of their own (with six-warp blocks the two kernels share SMs).
+    if (cnt <= (progress ? (size_t)ctx->coop12_piped_max : sms) && ctx->coop12 && ctx->pairing_mode == 0) {
+      k_coop12_run<<<(unsigned)cnt, COOP12_THREADS, COOP12_SMEM_BYTES, ctx->stream>>>(which, n > i0 ? n - i0 : 0, n_pad, lines + i0,
+                                                                                    gslots ? gslots + i0 : gslots, fio ? fio + i0 : fio,
+                                                                                    status ? status + i0 : status, progress ? progress + i0 : progress);
+      ctx->launches++;
+      return;
+    }
     k_coop_run<<<(unsigned)cnt, COOP_THREADS, COOP1_SMEM_BYTES, ctx->stream>>>(which, n > i0 ? n - i0 : 0, n_pad, lines + i0, gslots ? gslots + i0 : gslots,
                                                                             fio ? fio + i0 : fio, status ? status + i0 : status, ctx->coop_stagger,
                                                                             (unsigned)sms, progress ? progress + i0 : progress);
@@ -1579,8 +1695,12 @@ static int verify_dev_impl(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, 
         CK(cudaMemsetAsync(PR.p, 0, sizeof(unsigned) * m_pad, ctx->stream));
         CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
         CK(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
-        k_verify_lines_lat<<<grid_for(m, 32), 32, 0, ctx->aux_stream>>>(h, sigs + 64 * off, pks + 128 * off, m, LN.as<u4>(), m_pad, status + off,
-                                                                        ctx->d_lines, PR.as<unsigned>());
+        if (ctx->lines_walk4)
+          k_verify_lines_walk4<<<(unsigned)(m_pad / COOP_LANES), WALK_WARPS * 32, WALK_SMEM_BYTES, ctx->aux_stream>>>(
+              h, sigs + 64 * off, pks + 128 * off, m, LN.as<u4>(), m_pad, status + off, ctx->d_lines, PR.as<unsigned>());
+        else
+          k_verify_lines_lat<<<grid_for(m, 32), 32, 0, ctx->aux_stream>>>(h, sigs + 64 * off, pks + 128 * off, m, LN.as<u4>(), m_pad, status + off,
+                                                                          ctx->d_lines, PR.as<unsigned>());
         ctx->launches++;
         CK(cudaGetLastError());
         CK(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
@@ -1592,7 +1712,12 @@ static int verify_dev_impl(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, 
         CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));  // everything after this call (frees included) is ordered after the producer
         continue;
       }
-      if (lat)
+      if (lat && ctx->lines_walk4) {
+        k_verify_lines_walk4<<<(unsigned)(m_pad / COOP_LANES), WALK_WARPS * 32, WALK_SMEM_BYTES, ctx->stream>>>(
+            h, sigs + 64 * off, pks + 128 * off, m, LN.as<u4>(), m_pad, status + off, ctx->d_lines, (unsigned*)nullptr);
+        ctx->launches++;
+        CK(cudaGetLastError());
+      } else if (lat)
         LAUNCH(k_verify_lines_lat, grid_for(m, 32), 32, h, sigs + 64 * off, pks + 128 * off, m, LN.as<u4>(), m_pad, status + off, ctx->d_lines,
                (unsigned*)nullptr);
       else
@@ -2342,14 +2467,18 @@ static int finish_payloads_dev(bn254_ctx* ctx, const uint8_t* payloads, size_t m
     LAUNCH(k_distinct_finish, 1, 32, payloads, (int)m, agg_sig, ctx->d_lines, status);
     return 0;
   }
-  // one item through the cooperative machine (six warps of one block): Miller loop over the 87 scaled -G2 lines of agg_sig,
+  // one item through the cooperative machine (one block, latency layout): Miller loop over the 87 scaled -G2 lines of agg_sig,
   // times the product of the records, final exponentiation, verdict
   DALLOC(LNf, sizeof(u4) * COOP_LINE_FQ * 2 * K_N_LINES * COOP_LANES);
   DALLOC(FIOf, sizeof(u4) * 6 * 2 * 2 * COOP_LANES);
   DALLOC(GSf, sizeof(u4) * COOP_GSLOTS * 6 * 2 * 2 * COOP_LANES);
   LAUNCH(k_finish_prepare, 1, BN_BLOCK, payloads, (int)m, agg_sig, ctx->d_lines, LNf.as<u4>(), FIOf.as<u4>(), status);
-  k_coop_run<<<1, COOP_THREADS, COOP1_SMEM_BYTES, ctx->stream>>>(CPROG_FINISH, (size_t)1, (size_t)COOP_LANES, LNf.as<u4>(), GSf.as<u4>(), FIOf.as<u4>(), status,
-                                                                0u, (unsigned)ctx->sm_count, (const unsigned*)nullptr);
+  if (ctx->coop12)
+    k_coop12_run<<<1, COOP12_THREADS, COOP12_SMEM_BYTES, ctx->stream>>>(CPROG_FINISH, (size_t)1, (size_t)COOP_LANES, LNf.as<u4>(), GSf.as<u4>(), FIOf.as<u4>(),
+                                                                        status, (const unsigned*)nullptr);
+  else
+    k_coop_run<<<1, COOP_THREADS, COOP1_SMEM_BYTES, ctx->stream>>>(CPROG_FINISH, (size_t)1, (size_t)COOP_LANES, LNf.as<u4>(), GSf.as<u4>(), FIOf.as<u4>(), status,
+                                                                  0u, (unsigned)ctx->sm_count, (const unsigned*)nullptr);
   ctx->launches++;
   CK(cudaGetLastError());
   return 0;

@@ -223,6 +223,247 @@ BN_FN int item_verify_lines(u4* lines, size_t n_pad, size_t item, const g1aff* h
   return item_verify_lines_t<lines_mul_call>(lines, n_pad, item, h, sig, pk, table, K);
 }
 
+// ---------------------------------------------------------------------------------------------- cooperative walk (small batches)
+// The walk above is one thread per item: 3083 Fq products one after the other, ~1.9 ms however small the batch.  Here FOUR warps
+// (one per sub-partition of an SM) share the walk of 32 items -- lane = item, as in the machine -- and every curve step is cut
+// into LEVELS of Fq2 operations that do not depend on each other, one operation (or two short ones) per warp and level, a block
+// barrier between levels; all values live in shared memory (slots of one Fq2 per lane, the machine's conflict-free [Fq][chunk][lane]
+// layout).  Same formulas, same canonical values as doubling_step_v / mixed_addition_step_v -- the line sets are bit-identical
+// (tests/test_hostsim.py compares the two producers) -- but the dependent chain of a doubling is 9 Fq products instead of 38 and
+// that of an addition 14 instead of 45.  The scaled lines of the fixed pair (sig, -G2) fill the idle slots of the first level.
+//   doubling   level 0: w0 a = x y / 2, j = x^2   w1 b = y^2, fixed l3   w2 c = z^2, e = b' 3c   w3 s = (y+z)^2, fixed l4
+//              level 1: w0 x' = a (b - f), l0     w1 y' = g^2 - 3 e^2    w2 z' = b h            w3 l3 = -h py, l4 = 3j px
+//   addition   level 0: w0 d = x - qx z           w1 e = y - qy z        w2 fixed l3             w3 fixed l4
+//              level 1: w0 f = d^2, h = d f       w1 g = e^2, z g        w2 e qx, l4 = -e px     w3 d qy, l3 = d py
+//              level 2: w0 i = x f                w1 t = h y             w2 z' = z h             w3 l0 = xi (e qx - d qy)
+//              level 3: w0 x' = d j               w1 y' = e (i - j) - t                          (j = h + z g - 2 i)
+enum {
+  WS_X, WS_Y, WS_Z, WS_QX, WS_QY, WS_NQY, WS_Q1X, WS_Q1Y, WS_Q2X, WS_Q2Y, WS_P, WS_SG,  // running point, the key and its images, (hx, hy), (sx, sy)
+  WS_A, WS_B, WS_CC, WS_E, WS_S, WS_J,                                                   // doubling
+  WS_D, WS_EE, WS_F, WS_RG, WS_H, WS_I, WS_T, WS_EQX, WS_DQY,                            // addition
+  WS_SLOTS
+};
+#define WALK_WARPS 4
+#define WALK_SMEM_BYTES (WS_SLOTS * 2 * 2 * COOP_LANES * 16 + 4 * COOP_LANES * 4) /* slots + per-lane decode results */
+struct walk_ctx {
+  u4* sm;         // the lane's column of the slot array
+  int* flags;     // [0][lane] status of the key, [1][lane] status of the signature, [2][lane] key at infinity, [3][lane] signature at infinity
+  int row, lane, warp;
+  size_t item, n, n_pad;
+  u4* lines;
+  const line_t* table;
+  bool live, use_a, use_b;  // (set after walk_decode's barrier)
+};
+BN_FN fq2 walk_ld(const walk_ctx& c, int s) {
+  fq2 r;
+  r.c0 = coop_ld(c.sm, 2 * s, c.row);
+  r.c1 = coop_ld(c.sm, 2 * s + 1, c.row);
+  return r;
+}
+BN_FN void walk_st(const walk_ctx& c, int s, const fq2& v) {
+  coop_st(c.sm, 2 * s, c.row, v.c0);
+  coop_st(c.sm, 2 * s + 1, c.row, v.c1);
+}
+// coefficient `which` (0: l0, 1: l3, 2: l4) of line set `set`, as the triple (x0, x1, x0 + x1) coop_emit_line writes
+BN_FN void walk_emit(const walk_ctx& c, size_t set, int which, bool use, fq2 v) {
+  if (!c.live) return;
+  if (!use) {
+    v = fq2_zero();
+    if (which == 0) v = fq2_one();
+  }
+  const size_t r = set * COOP_LINE_FQ + 3 * which;
+  coop_gst(c.lines, r + 0, c.n_pad, c.item, v.c0);
+  coop_gst(c.lines, r + 1, c.n_pad, c.item, v.c1);
+  coop_gst(c.lines, r + 2, c.n_pad, c.item, fq_add(v.c0, v.c1));
+}
+// half of the fixed pair's line set 2m + 1: warp `half` = 0 writes l0 and l3 = ell_vw sy, 1 writes l4 = ell_vv sx
+template <class M>
+BN_FN void walk_fixed(const walk_ctx& c, size_t m, int half) {
+  const fq2 sg = walk_ld(c, WS_SG);
+  if (half == 0) {
+    walk_emit(c, 2 * m + 1, 0, c.use_b, c.table[m].ell_0);
+    walk_emit(c, 2 * m + 1, 1, c.use_b, M::scale(c.table[m].ell_vw, sg.c1));
+  } else {
+    walk_emit(c, 2 * m + 1, 2, c.use_b, M::scale(c.table[m].ell_vv, sg.c0));
+  }
+}
+// decode: warp 0 the key (and its two Frobenius images), warp 1 the signature and the G1 point of the variable pair
+BN_FN void walk_decode(const walk_ctx& c, const g1aff* h, const uint8_t* sig, const uint8_t* pk, bool skip) {
+  if (c.warp == 0) {
+    g2j q;
+    int st = skip ? ST_OK : g2_from_raw(&q, pk);
+    if (skip || st) pt_set_inf(&q);
+    c.flags[0 * COOP_LANES + c.lane] = st;
+    c.flags[2 * COOP_LANES + c.lane] = pt_is_inf(&q) ? 1 : 0;
+    fq2 q1x, q1y, q2x, q2y;
+    g2_frobenius_pair(&q1x, &q1y, &q2x, &q2y, q.x, q.y);
+    walk_st(c, WS_QX, q.x);
+    walk_st(c, WS_QY, q.y);
+    walk_st(c, WS_NQY, fq2_neg(q.y));
+    walk_st(c, WS_Q1X, q1x);
+    walk_st(c, WS_Q1Y, q1y);
+    walk_st(c, WS_Q2X, q2x);
+    walk_st(c, WS_Q2Y, q2y);
+    walk_st(c, WS_X, q.x);
+    walk_st(c, WS_Y, q.y);
+    walk_st(c, WS_Z, fq2_one());
+  } else if (c.warp == 1) {
+    g1j s;
+    int st = skip ? ST_OK : g1_from_raw(&s, sig);
+    if (skip || st) pt_set_inf(&s);
+    c.flags[1 * COOP_LANES + c.lane] = st;
+    c.flags[3 * COOP_LANES + c.lane] = pt_is_inf(&s) ? 1 : 0;
+    fq2 t;
+    t.c0 = s.x;
+    t.c1 = s.y;
+    walk_st(c, WS_SG, t);
+    if (!skip) {
+      t.c0 = h->x;
+      t.c1 = h->y;
+    }
+    walk_st(c, WS_P, t);
+  }
+}
+// status of the item as item_verify_lines returns it (key first); fills the context's flags.  Call after the barrier behind walk_decode.
+BN_FN int walk_flags(walk_ctx& c, bool skip) {
+  const int st_pk = c.flags[0 * COOP_LANES + c.lane], st_sig = c.flags[1 * COOP_LANES + c.lane];
+  const int st = st_pk ? st_pk : st_sig;
+  c.live = !skip && st == ST_OK;
+  c.use_a = c.flags[2 * COOP_LANES + c.lane] == 0;
+  c.use_b = c.flags[3 * COOP_LANES + c.lane] == 0;
+  return st;
+}
+template <class M>
+BN_FN void walk_dbl(const walk_ctx& c, int level, size_t m) {
+  if (level == 0) {
+    if (c.warp == 0) {
+      const fq2 x = walk_ld(c, WS_X);
+      fq2 a = M::mul(x, walk_ld(c, WS_Y));
+      a.c0 = fq_halve(a.c0);
+      a.c1 = fq_halve(a.c1);
+      walk_st(c, WS_A, a);
+      walk_st(c, WS_J, M::sqr(x));
+    } else if (c.warp == 1) {
+      walk_st(c, WS_B, M::sqr(walk_ld(c, WS_Y)));
+      walk_fixed<M>(c, m, 0);
+    } else if (c.warp == 2) {
+      const fq2 cc = M::sqr(walk_ld(c, WS_Z));
+      walk_st(c, WS_CC, cc);
+      walk_st(c, WS_E, M::mul(fq2_from_limbs(K_TWIST_B), fq2_add(fq2_dbl(cc), cc)));
+    } else {
+      walk_st(c, WS_S, M::sqr(fq2_add(walk_ld(c, WS_Y), walk_ld(c, WS_Z))));
+      walk_fixed<M>(c, m, 1);
+    }
+    return;
+  }
+  const fq2 b = walk_ld(c, WS_B);
+  if (c.warp == 0) {
+    const fq2 e = walk_ld(c, WS_E);
+    const fq2 f = fq2_add(fq2_dbl(e), e);
+    walk_st(c, WS_X, M::mul(walk_ld(c, WS_A), fq2_sub(b, f)));
+    walk_emit(c, 2 * m, 0, c.use_a, fq2_mul_xi(fq2_sub(e, b)));
+  } else if (c.warp == 1) {
+    const fq2 e = walk_ld(c, WS_E);
+    const fq2 f = fq2_add(fq2_dbl(e), e);
+    fq2 g = fq2_add(b, f);
+    g.c0 = fq_halve(g.c0);
+    g.c1 = fq_halve(g.c1);
+    const fq2 e2 = M::sqr(e);
+    walk_st(c, WS_Y, fq2_sub(M::sqr(g), fq2_add(fq2_dbl(e2), e2)));
+  } else {
+    const fq2 h = fq2_sub(walk_ld(c, WS_S), fq2_add(b, walk_ld(c, WS_CC)));
+    if (c.warp == 2) {
+      walk_st(c, WS_Z, M::mul(b, h));
+    } else {
+      const fq2 p = walk_ld(c, WS_P);
+      const fq2 j = walk_ld(c, WS_J);
+      walk_emit(c, 2 * m, 1, c.use_a, M::scale(fq2_neg(h), p.c1));
+      walk_emit(c, 2 * m, 2, c.use_a, M::scale(fq2_add(fq2_dbl(j), j), p.c0));
+    }
+  }
+}
+template <class M>
+BN_FN void walk_add(const walk_ctx& c, int level, size_t m, int sqx, int sqy) {
+  switch (level) {
+    case 0:
+      if (c.warp == 0)
+        walk_st(c, WS_D, fq2_sub(walk_ld(c, WS_X), M::mul(walk_ld(c, sqx), walk_ld(c, WS_Z))));
+      else if (c.warp == 1)
+        walk_st(c, WS_EE, fq2_sub(walk_ld(c, WS_Y), M::mul(walk_ld(c, sqy), walk_ld(c, WS_Z))));
+      else
+        walk_fixed<M>(c, m, c.warp - 2);
+      break;
+    case 1:
+      if (c.warp == 0) {
+        const fq2 d = walk_ld(c, WS_D);
+        const fq2 f = M::sqr(d);
+        walk_st(c, WS_F, f);
+        walk_st(c, WS_H, M::mul(d, f));
+      } else if (c.warp == 1) {
+        walk_st(c, WS_RG, M::mul(walk_ld(c, WS_Z), M::sqr(walk_ld(c, WS_EE))));
+      } else if (c.warp == 2) {
+        const fq2 e = walk_ld(c, WS_EE);
+        walk_st(c, WS_EQX, M::mul(e, walk_ld(c, sqx)));
+        walk_emit(c, 2 * m, 2, c.use_a, M::scale(fq2_neg(e), walk_ld(c, WS_P).c0));
+      } else {
+        const fq2 d = walk_ld(c, WS_D);
+        walk_st(c, WS_DQY, M::mul(d, walk_ld(c, sqy)));
+        walk_emit(c, 2 * m, 1, c.use_a, M::scale(d, walk_ld(c, WS_P).c1));
+      }
+      break;
+    case 2:
+      if (c.warp == 0)
+        walk_st(c, WS_I, M::mul(walk_ld(c, WS_X), walk_ld(c, WS_F)));
+      else if (c.warp == 1)
+        walk_st(c, WS_T, M::mul(walk_ld(c, WS_H), walk_ld(c, WS_Y)));
+      else if (c.warp == 2)
+        walk_st(c, WS_Z, M::mul(walk_ld(c, WS_Z), walk_ld(c, WS_H)));
+      else
+        walk_emit(c, 2 * m, 0, c.use_a, fq2_mul_xi(fq2_sub(walk_ld(c, WS_EQX), walk_ld(c, WS_DQY))));
+      break;
+    default:
+      if (c.warp < 2) {
+        const fq2 i = walk_ld(c, WS_I);
+        const fq2 j = fq2_sub(fq2_add(walk_ld(c, WS_H), walk_ld(c, WS_RG)), fq2_dbl(i));
+        if (c.warp == 0)
+          walk_st(c, WS_X, M::mul(walk_ld(c, WS_D), j));
+        else
+          walk_st(c, WS_Y, fq2_sub(M::mul(walk_ld(c, WS_EE), fq2_sub(i, j)), walk_ld(c, WS_T)));
+      }
+      break;
+  }
+}
+// The schedule of the 87 steps: step(kind, level, m, sqx, sqy) for every level, bar() behind every level, done(m) once step m - 1
+// is complete (all of its line-set stores are before the last bar()).
+template <class Step, class Bar, class Done>
+BN_FN void walk_schedule(Step step, Bar bar, Done done) {
+  size_t m = 0;
+  auto dbl = [&] {
+    for (int l = 0; l < 2; l++) {
+      step(0, l, m, 0, 0);
+      bar();
+    }
+    done(++m);
+  };
+  auto add = [&](int sqx, int sqy) {
+    for (int l = 0; l < 4; l++) {
+      step(1, l, m, sqx, sqy);
+      bar();
+    }
+    done(++m);
+  };
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+  for (int k = 0; k < 64; k++) {
+    dbl();
+    const int d = K_ATE_DIGITS[k];
+    if (d != 0) add(WS_QX, d > 0 ? WS_QY : WS_NQY);
+  }
+  add(WS_Q1X, WS_Q1Y);
+  add(WS_Q2X, WS_Q2Y);
+}
+
 // Multi-pairing producer: pair (h, pk) is stream `stream` of its lane `item`; its 87 line sets go to set index
 // step * mk + stream (mk = pairs per lane of the program that will consume them).  use == false (padding slot, pk at infinity, or an item that failed to decode) writes the
 // constant 1 everywhere, which leaves the lane's product unchanged.

@@ -334,7 +334,8 @@ enum {
   ST_POINT_IN_JACOBIAN = 8,
   ST_VERIFICATION_FAILED = 9,
   ST_SERIALIZATION = 10,
-  ST_HEX_DECODE = 11
+  ST_HEX_DECODE = 11,
+  ST_ENGINE_FAULT = 255  // not an Error variant: the item was NOT evaluated (pipelined small-batch verify: its line sets never arrived)
 };
 
 BN_FN bool bytes_all_zero(const uint8_t* b, int n) {

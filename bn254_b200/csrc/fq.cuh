@@ -258,6 +258,27 @@ BN_FN fq fq_csub(const fq& a) {
 #endif
 BN_FN fq fq_dbl(const fq& a) { return fq_add(a, a); }
 BN_FN fq fq_neg(const fq& a) { return fq_sub(fq_zero(), a); }
+// a / 2 (valid on Montgomery representatives as well: the map is linear): (a + (a odd ? q : 0)) >> 1, canonical, no product
+BN_FN fq fq_halve(const fq& a) {
+  const uint32_t qq[8] = {BN_Q0, BN_Q1, BN_Q2, BN_Q3, BN_Q4, BN_Q5, BN_Q6, BN_Q7};
+  const uint32_t odd = 0u - (a.l[0] & 1u);
+  uint32_t t[8];
+  uint64_t c = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < 8; i++) {
+    c += (uint64_t)a.l[i] + (qq[i] & odd);
+    t[i] = (uint32_t)c;
+    c >>= 32;
+  }
+  fq r;  // a + q < 2^255: nothing above t[7]
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < 8; i++) r.l[i] = (t[i] >> 1) | (i < 7 ? t[i + 1] << 31 : 0u);
+  return r;
+}
 
 #define BN_KQ_RECIP 0xa948e8c0u /* floor(2^59 / ((q >> 226) + 1)) */
 // t (nine limbs, below 11 q) mod q: quotient estimate from the top bits, k q from the table, one conditional subtraction

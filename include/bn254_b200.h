@@ -46,7 +46,10 @@ enum {
   BN254_POINT_IN_JACOBIAN = 8,
   BN254_VERIFICATION_FAILED = 9,
   BN254_SERIALIZATION_ERROR = 10,
-  BN254_HEX_DECODE_FAILED = 11
+  BN254_HEX_DECODE_FAILED = 11,
+  /* not an Error variant: the engine did NOT evaluate the item (the producer / machine handshake of the pipelined small-batch
+   * verify timed out -- never observed; it exists so that such an item is reported instead of guessed).  Retry the call. */
+  BN254_ENGINE_FAULT = 255
 };
 
 /* engine-level errors (function return values) */

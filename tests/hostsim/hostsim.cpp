@@ -318,6 +318,68 @@ API int hs_coop_verify(const uint8_t* msg, size_t len, const uint8_t* sig, const
   S.run(K_COOP_PROG_VERIFY);
   return S.status;
 }
+// The cooperative walk (coop_lines.cuh walk_*), simulated: per level every (warp, lane) in turn, a barrier = the end of the sweep.
+// Fills the line sets of lane 0 .. lanes - 1 (each lane gets the same item) and returns the item's status.
+static int walk4_sim(std::vector<u4>& lines, size_t n_pad, int lanes, const g1aff* h, const uint8_t* sig, const uint8_t* pk) {
+  std::vector<u4> sm(WS_SLOTS * 2 * 2 * COOP_LANES);
+  std::vector<int> flags(4 * COOP_LANES);
+  auto ctx = [&](int w, int l) {
+    walk_ctx c;
+    c.sm = sm.data() + l; c.flags = flags.data(); c.row = COOP_LANES; c.lane = l; c.warp = w;
+    c.item = (size_t)l; c.n = (size_t)lanes; c.n_pad = n_pad; c.lines = lines.data(); c.table = g_lines;
+    c.live = c.use_a = c.use_b = false;
+    return c;
+  };
+  for (int w = 0; w < WALK_WARPS; w++)
+    for (int l = 0; l < lanes; l++) walk_decode(ctx(w, l), h, sig, pk, false);
+  int st = 0;
+  {
+    walk_ctx c = ctx(0, 0);
+    st = walk_flags(c, false);
+  }
+  int steps_done = 0;
+  walk_schedule(
+      [&](int kind, int level, size_t m, int sqx, int sqy) {
+        for (int w = 0; w < WALK_WARPS; w++)
+          for (int l = 0; l < lanes; l++) {
+            walk_ctx c = ctx(w, l);
+            walk_flags(c, false);
+            if (kind == 0) walk_dbl<lines_mul_call>(c, level, m); else walk_add<lines_mul_call>(c, level, m, sqx, sqy);
+          }
+      },
+      [] {}, [&](size_t m) { steps_done = (int)m; });
+  if (steps_done != K_N_LINES) return -1;
+  return st;
+}
+// both producers on one item: 0 = same status and (status OK) bit-identical line sets; out_status = the status
+API int hs_walk4_matches(const uint8_t* msg, size_t len, const uint8_t* sig, const uint8_t* pk, int* out_status) {
+  ensure_init();
+  g1aff h;
+  int st = hash_to_g1(&h.x, &h.y, msg, len, nullptr);
+  if (st) return -2;
+  const size_t n_pad = COOP_LANES, words = (size_t)2 * K_N_LINES * COOP_LINE_FQ * 2 * n_pad;
+  u4 zero; zero.x = zero.y = zero.z = zero.w = 0;
+  std::vector<u4> a(words, zero), b(words, zero);
+  lines_consts K;
+  const int st_a = item_verify_lines(a.data(), n_pad, 0, &h, sig, pk, g_lines, &K);
+  const int st_b = walk4_sim(b, n_pad, 1, &h, sig, pk);
+  *out_status = st_b;
+  if (st_a != st_b) return 1;
+  if (st_a) return 0;
+  return memcmp(a.data(), b.data(), words * sizeof(u4)) == 0 ? 0 : 2;
+}
+// full verify with the cooperative walk as the producer of the machine's line sets
+API int hs_coop_verify_walk4(const uint8_t* msg, size_t len, const uint8_t* sig, const uint8_t* pk) {
+  ensure_init();
+  g1aff h;
+  int st = hash_to_g1(&h.x, &h.y, msg, len, nullptr);
+  if (st) return st;
+  coop_sim S;
+  st = walk4_sim(S.lines, S.n_pad, 1, &h, sig, pk);
+  if (st) return st;
+  S.run(K_COOP_PROG_VERIFY);
+  return S.status;
+}
 // Miller product of the verify pairs (tower order, big-endian) through the cooperative program
 API int hs_coop_verify_miller(const uint8_t* msg, size_t len, const uint8_t* sig, const uint8_t* pk, uint8_t* f_out) {
   ensure_init();

@@ -307,6 +307,31 @@ def test_coop_verify_matches_oracle(hs, layout):
         assert hs.hs_coop_verify(b"", 0, O.derive_pk_g1(H(v["sk_g1"]))[1], O.derive_pk_g2(H(v["sk_g2"]))[1], 1) == O.VERIFICATION_FAILED
 
 
+def test_cooperative_walk_matches_one_thread_walk(hs):
+    """The four-warp producer of small batches (coop_lines.cuh walk_*) writes the SAME 174 line sets, bit for bit, as the
+    one-thread-per-item producer, returns the same decode statuses, and the machine run on its sets agrees with the oracle."""
+    import ctypes
+    rng = random.Random(29)
+    st = ctypes.c_int(0)
+    sk = be(rng.randrange(1, R))
+    msg = rng.randbytes(32)
+    sig, pk = O.sign(msg, sk)[1], O.derive_pk_g2(sk)[1]
+    for t in range(3):
+        sk = be(rng.randrange(1, R))
+        msg = rng.randbytes(1 + 40 * t)
+        sig, pk = O.sign(msg, sk)[1], O.derive_pk_g2(sk)[1]
+        assert hs.hs_walk4_matches(msg, len(msg), sig, pk, ctypes.byref(st)) == 0 and st.value == 0
+    assert hs.hs_coop_verify_walk4(msg, len(msg), sig, pk) == 0
+    assert hs.hs_coop_verify_walk4(msg, len(msg), O.g1_add(sig, G1_GEN)[1], pk) == O.VERIFICATION_FAILED
+    # infinities (constant line sets) and decode errors
+    for s_, p_ in ((bytes(64), bytes(128)), (bytes(64), pk), (sig, bytes(128))):
+        assert hs.hs_walk4_matches(msg, len(msg), s_, p_, ctypes.byref(st)) == 0 and st.value == 0
+        assert hs.hs_coop_verify_walk4(msg, len(msg), s_, p_) == O.verify(msg, s_, p_)
+    assert hs.hs_walk4_matches(msg, len(msg), be(1) + be(3), pk, ctypes.byref(st)) == 0 and st.value == O.INVALID_GROUP_POINT
+    bad_pk = pk[:127] + bytes([pk[127] ^ 1])
+    assert hs.hs_walk4_matches(msg, len(msg), sig, bad_pk, ctypes.byref(st)) == 0 and st.value == O.verify(msg, sig, bad_pk) != 0
+
+
 def test_coop_multi_pairing_program(hs):
     """COOP_MULTI_K pairs per lane share one squaring chain, then the 32 lanes are multiplied by a butterfly: the block's
     product equals the oracle's Miller product over all pairs (canonical field values, any multiplication order)."""
