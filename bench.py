@@ -362,7 +362,7 @@ def run_engine(args):
 
         # small-batch latency of the crate's own call shape: host buffers in, verdicts out, one call at a time
         lat = {}
-        for nl in (1, 32, 1024, 1 << 14):
+        for nl in (1, 2, 4, 32, 1024, 4736, 1 << 14):
             if nl > n:
                 continue
             hm, hs_, hp = h_msgs[:32 * nl], h_sigs[:64 * nl], h_pks[:128 * nl]
@@ -436,7 +436,7 @@ def run_engine(args):
             lat = configs["latency_verify_host_buffers"]
             lat["cpu_port_one_core_ms_per_verify"] = one
             # the batch size from which one GPU call beats one CPU core doing the items one after the other
-            lat["crossover_items_vs_one_cpu_core"] = next((int(k) for k in ("1", "32", "1024", "16384") if k in lat and lat[k]["ms_median"] < int(k) * one), None)
+            lat["crossover_items_vs_one_cpu_core"] = next((int(k) for k in ("1", "2", "4", "32", "1024", "4736", "16384") if k in lat and lat[k]["ms_median"] < int(k) * one), None)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",

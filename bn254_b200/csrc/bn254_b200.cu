@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, 4) k_verify_lines_walk4(const
   extern __shared__ u4 walk_sm[];
   walk_ctx c;
   c.lane = threadIdx.x & 31;
-  c.warp = threadIdx.x >> 5;
+  c.warp = ((threadIdx.x >> 5) + blockIdx.x) % WALK_WARPS;  // role of this warp: rotated, so that co-resident blocks load the sub-partitions evenly
   c.sm = walk_sm + c.lane;
   c.flags = (int*)(walk_sm + WS_SLOTS * 2 * 2 * COOP_LANES);
   c.row = COOP_LANES;
@@ -1230,6 +1230,7 @@ struct bn254_ctx {
   cudaStream_t aux_stream = nullptr;   // small-batch verify: the line producer runs here WHILE the machine consumes its line sets
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool pipeline_small = true;          // BN254_PIPELINE=0 turns the producer / machine overlap off (measurement)
+  size_t lines_lat_max = 0;            // largest launch that uses the small-batch producer (default 64 items per SM; BN254_LINES_LAT_MAX)
   bool lines_walk4 = true;             // BN254_LINES_WALK4=0: small batches use the one-thread-per-item latency producer (measurement)
   int coop12_piped_max = 1 << 30;      // BN254_COOP12_PIPED_MAX: most groups of a PIPELINED launch that still get twelve-warp blocks
   bool coop12 = true;                  // BN254_COOP12=0: six-warp blocks even when a group has an SM to itself (measurement)
@@ -1335,6 +1336,8 @@ int bn254_ctx_create(int device, bn254_ctx** out) {
   if (const char* w = getenv("BN254_COOP12")) ctx->coop12 = w[0] != '0';
   if (const char* w = getenv("BN254_COOP12_PIPED_MAX")) ctx->coop12_piped_max = atoi(w);
   if (const char* w = getenv("BN254_LINES_WALK4")) ctx->lines_walk4 = w[0] != '0';
+  ctx->lines_lat_max = (size_t)ctx->sm_count * 64;
+  if (const char* w = getenv("BN254_LINES_LAT_MAX")) ctx->lines_lat_max = (size_t)atoll(w);
   if ((e = cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
   // A private pool (the device's default pool is shared with the host process, e.g. torch): freed blocks stay cached here
   // between calls -- the line-set workspace of verify is allocated once, not per call -- and everything is returned to the
@@ -1683,7 +1686,7 @@ static int verify_dev_impl(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, 
       size_t m_pad = (m + COOP_LANES - 1) / COOP_LANES * COOP_LANES;
       // small batches: every warp is alone on its sub-partition and bound by the latency of its dependent carry chains -> the
       // form with three products in flight (profiles/r02_tuning_log.md section 4); big batches: the compact form
-      const bool lat = m <= (size_t)ctx->sm_count * 64 && !ctx->lines_throughput_only;
+      const bool lat = m <= (size_t)ctx->lines_lat_max && !ctx->lines_throughput_only;
       // At most one group per SM, default layout: producer and machine run CONCURRENTLY.  The producer (aux stream) publishes,
       // per item, how many Miller steps' line sets are in memory; the machine waits for a step's count before it fetches the
       // step's sets, so its Miller loop hides under the walk and only the final exponentiation is left after it.  Both grids

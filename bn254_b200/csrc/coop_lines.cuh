@@ -86,17 +86,31 @@ typedef lines_mul_call lines_mul_ilp;
 typedef lines_mul_call lines_mul_flat;
 #endif
 
-// the two curve steps of pairing.cuh with every Fq2 value passed in registers (same formulas, same results)
+BN_FN fq2 fq2_halve(const fq2& a) {
+  fq2 r;
+  r.c0 = fq_halve(a.c0);
+  r.c1 = fq_halve(a.c1);
+  return r;
+}
+// the two curve steps of pairing.cuh with every Fq2 value passed in registers (same formulas, same results; x / 2 as a shift)
 template <class M>
 BN_FN void doubling_step_v(fq2& rx, fq2& ry, fq2& rz, fq2& ell_0, fq2& ell_vw, fq2& ell_vv) {
-  const fq two_inv = fq_from_limbs(K_TWO_INV);
   const fq2 twist_b = fq2_from_limbs(K_TWIST_B);
+#if defined(BN_LINES_SCALE_HALF)  // the two halvings as products by 1/2 (pairing.cuh's form; four Fq products more per doubling)
+  const fq two_inv = fq_from_limbs(K_TWO_INV);
   fq2 a = M::scale(M::mul(rx, ry), two_inv);
+#else
+  fq2 a = fq2_halve(M::mul(rx, ry));
+#endif
   fq2 b = M::sqr(ry);
   fq2 cc = M::sqr(rz);
   fq2 e = M::mul(twist_b, fq2_add(fq2_dbl(cc), cc));
   fq2 f = fq2_add(fq2_dbl(e), e);
+#if defined(BN_LINES_SCALE_HALF)
   fq2 g = M::scale(fq2_add(b, f), two_inv);
+#else
+  fq2 g = fq2_halve(fq2_add(b, f));
+#endif
   fq2 h = fq2_sub(M::sqr(fq2_add(ry, rz)), fq2_add(b, cc));
   fq2 j = M::sqr(rx);
   fq2 e2 = M::sqr(e);
@@ -338,10 +352,7 @@ BN_FN void walk_dbl(const walk_ctx& c, int level, size_t m) {
   if (level == 0) {
     if (c.warp == 0) {
       const fq2 x = walk_ld(c, WS_X);
-      fq2 a = M::mul(x, walk_ld(c, WS_Y));
-      a.c0 = fq_halve(a.c0);
-      a.c1 = fq_halve(a.c1);
-      walk_st(c, WS_A, a);
+      walk_st(c, WS_A, fq2_halve(M::mul(x, walk_ld(c, WS_Y))));
       walk_st(c, WS_J, M::sqr(x));
     } else if (c.warp == 1) {
       walk_st(c, WS_B, M::sqr(walk_ld(c, WS_Y)));
@@ -365,9 +376,7 @@ BN_FN void walk_dbl(const walk_ctx& c, int level, size_t m) {
   } else if (c.warp == 1) {
     const fq2 e = walk_ld(c, WS_E);
     const fq2 f = fq2_add(fq2_dbl(e), e);
-    fq2 g = fq2_add(b, f);
-    g.c0 = fq_halve(g.c0);
-    g.c1 = fq_halve(g.c1);
+    const fq2 g = fq2_halve(fq2_add(b, f));
     const fq2 e2 = M::sqr(e);
     walk_st(c, WS_Y, fq2_sub(M::sqr(g), fq2_add(fq2_dbl(e2), e2)));
   } else {
