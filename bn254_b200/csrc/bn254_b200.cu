@@ -377,7 +377,9 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, 4) k_verify_lines_walk4(const
   extern __shared__ u4 walk_sm[];
   walk_ctx c;
   c.lane = threadIdx.x & 31;
-  c.warp = ((threadIdx.x >> 5) + blockIdx.x) % WALK_WARPS;  // role of this warp: rotated, so that co-resident blocks load the sub-partitions evenly
+  // role = warp index.  (Rotating the roles with the block index, to even out the sub-partitions when several blocks share an SM,
+  // was measured: no gain as a throughput producer, and 8 % slower next to a twelve-warp machine block -- r02 tuning log.)
+  c.warp = threadIdx.x >> 5;
   c.sm = walk_sm + c.lane;
   c.flags = (int*)(walk_sm + WS_SLOTS * 2 * 2 * COOP_LANES);
   c.row = COOP_LANES;
@@ -1232,7 +1234,7 @@ struct bn254_ctx {
   bool pipeline_small = true;          // BN254_PIPELINE=0 turns the producer / machine overlap off (measurement)
   size_t lines_lat_max = 0;            // largest launch that uses the small-batch producer (default 64 items per SM; BN254_LINES_LAT_MAX)
   bool lines_walk4 = true;             // BN254_LINES_WALK4=0: small batches use the one-thread-per-item latency producer (measurement)
-  int coop12_piped_max = 1 << 30;      // BN254_COOP12_PIPED_MAX: most groups of a PIPELINED launch that still get twelve-warp blocks
+  size_t piped_max_groups = 0;         // most groups of a pipelined verify (default: 3/4 of the SMs; BN254_PIPED_MAX_GROUPS)
   bool coop12 = true;                  // BN254_COOP12=0: six-warp blocks even when a group has an SM to itself (measurement)
   line_t* d_lines = nullptr;
   aff<fq>* d_comb_g1 = nullptr;   // (d + 1) * 16^w * G1 generator
@@ -1334,7 +1336,9 @@ int bn254_ctx_create(int device, bn254_ctx** out) {
   if ((e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
   if (const char* w = getenv("BN254_PIPELINE")) ctx->pipeline_small = w[0] != '0';
   if (const char* w = getenv("BN254_COOP12")) ctx->coop12 = w[0] != '0';
-  if (const char* w = getenv("BN254_COOP12_PIPED_MAX")) ctx->coop12_piped_max = atoi(w);
+  ctx->piped_max_groups = (size_t)(ctx->sm_count - ctx->sm_count / 4);
+  if (const char* w = getenv("BN254_PIPED_MAX_GROUPS")) ctx->piped_max_groups = (size_t)atoll(w);
+  if (ctx->piped_max_groups > (size_t)ctx->sm_count) ctx->piped_max_groups = (size_t)ctx->sm_count;
   if (const char* w = getenv("BN254_LINES_WALK4")) ctx->lines_walk4 = w[0] != '0';
   ctx->lines_lat_max = (size_t)ctx->sm_count * 64;
   if (const char* w = getenv("BN254_LINES_LAT_MAX")) ctx->lines_lat_max = (size_t)atoll(w);
@@ -1588,10 +1592,8 @@ static int launch_coop_groups(bn254_ctx* ctx, int which, size_t n, size_t n_pad,
   const size_t sms = (size_t)ctx->sm_count;
   auto one_group_blocks = [&](size_t g0, size_t cnt) {  // groups g0 .. g0 + cnt - 1, one block each
     const size_t i0 = g0 * COOP_LANES;
-    // a group has an SM to itself: twelve warps per group (latency layout).  Pipelined, only up to half the SMs: a twelve-warp
-    // block leaves 4096 registers per sub-partition, a producer warp needs up to 8192 -- producer blocks cannot become resident
-    // NEXT to such a block, they need SMs of their own (with six-warp blocks the two kernels share SMs).
-    if (cnt <= (progress ? (size_t)ctx->coop12_piped_max : sms) && ctx->coop12 && ctx->pairing_mode == 0) {
+    // a group has an SM to itself: twelve warps per group (latency layout)
+    if (cnt <= sms && ctx->coop12 && ctx->pairing_mode == 0) {
       k_coop12_run<<<(unsigned)cnt, COOP12_THREADS, COOP12_SMEM_BYTES, ctx->stream>>>(which, n > i0 ? n - i0 : 0, n_pad, lines + i0,
                                                                                     gslots ? gslots + i0 : gslots, fio ? fio + i0 : fio,
                                                                                     status ? status + i0 : status, progress ? progress + i0 : progress);
@@ -1687,12 +1689,15 @@ static int verify_dev_impl(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, 
       // small batches: every warp is alone on its sub-partition and bound by the latency of its dependent carry chains -> the
       // form with three products in flight (profiles/r02_tuning_log.md section 4); big batches: the compact form
       const bool lat = m <= (size_t)ctx->lines_lat_max && !ctx->lines_throughput_only;
-      // At most one group per SM, default layout: producer and machine run CONCURRENTLY.  The producer (aux stream) publishes,
-      // per item, how many Miller steps' line sets are in memory; the machine waits for a step's count before it fetches the
-      // step's sets, so its Miller loop hides under the walk and only the final exponentiation is left after it.  Both grids
-      // fit the GPU together (<= 148 one-warp blocks + <= 148 six-warp blocks), so neither can starve the other.
+      // Small launches, default layout: producer and machine run CONCURRENTLY.  The producer (aux stream) publishes, per item, how
+      // many Miller steps' line sets are in memory; the machine waits for a step's count before it fetches the step's sets, so the
+      // walk hides under the Miller loop.  A machine block and a producer block fit one SM together (registers per sub-partition:
+      // 3 x 4096 + 4096; shared memory 66 + 55 KB), but nothing here DEPENDS on that: the launch is pipelined only while it leaves
+      // a quarter of the SMs free of machine blocks, so producer blocks (four fit an empty SM) always have somewhere to run, whichever
+      // kernel the hardware dispatches first.  Launches of more groups run the two kernels one after the other (measured: from
+      // ~120 groups on that is also the faster order, the two kernels then compete for the same multipliers).
       const bool piped = lat && !wl && !hl && ctx->pairing_mode == 0 && ctx->coop_groups4 && ctx->pipeline_small && !ctx->prof && n <= CHUNK &&
-                         m_pad / COOP_LANES <= (size_t)ctx->sm_count;
+                         m_pad / COOP_LANES <= ctx->piped_max_groups;
       if (piped) {
         DALLOC(PR, sizeof(unsigned) * m_pad);
         CK(cudaMemsetAsync(PR.p, 0, sizeof(unsigned) * m_pad, ctx->stream));
