@@ -502,19 +502,19 @@ __global__ void __launch_bounds__(COOP_THREADS, BN_COOP_MINB) k_coop_run(int whi
 
 // ---- latency layout (coop.cuh coop_run_block12): one 32-item group per TWELVE-warp block, for launches of at most one group per SM
 #define COOP12_THREADS (2 * COOP_THREADS)
-// group slots + six exchange slots + the k q table = 61 792 bytes, REQUESTED as 66 KB: a block of this kernel fills an SM's register
+// group slots + twelve exchange slots + the k q table = 67 936 bytes, REQUESTED as 68 KB (anything above 64 KB would do): a block of this kernel fills an SM's register
 // file to 3/4, so the driver would pick the smallest shared-memory carve-out that holds one block (64 KB) and leave 1 KB over --
 // and a pipelined producer block (10 KB) dispatched behind the machine could then never become resident next to it while the
-// machine waits for its line sets.  66 KB forces the 100 KB carve-out (or larger) on every configuration the SM has.
-#define COOP12_SMEM_USED (COOP_SMEM_BYTES + 6 * 2 * COOP_LANES * 16 + 11 * 32)
-#define COOP12_SMEM_BYTES (66 * 1024)
+// machine waits for its line sets.  More than 64 KB forces the 100 KB carve-out (or larger) on every configuration the SM has.
+#define COOP12_SMEM_USED (COOP_SMEM_BYTES + 12 * 2 * COOP_LANES * 16 + 11 * 32) /* (twelve exchange slots: the eighteen-warp form uses all of them) */
+#define COOP12_SMEM_BYTES (68 * 1024)
 static_assert(COOP12_SMEM_USED <= COOP12_SMEM_BYTES, "latency layout: shared memory");
-__global__ void __launch_bounds__(COOP12_THREADS, 1) k_coop12_run(int which, size_t n, size_t n_pad, const u4* __restrict__ lines,
-                                                                  u4* __restrict__ gslots, u4* __restrict__ fio, uint8_t* __restrict__ status,
-                                                                  const unsigned* progress) {
+template <int SPLIT>
+__device__ __forceinline__ void coop12_body(int which, size_t n, size_t n_pad, const u4* __restrict__ lines, u4* __restrict__ gslots, u4* __restrict__ fio,
+                                            uint8_t* __restrict__ status, const unsigned* progress) {
   extern __shared__ u4 coop_sm[];
   u4* xch_base = coop_sm + COOP_SLOTS * 2 * COOP_LANES;
-  uint32_t* kq = (uint32_t*)(xch_base + 6 * 2 * COOP_LANES);
+  uint32_t* kq = (uint32_t*)(xch_base + 12 * 2 * COOP_LANES);
   if (threadIdx.x < 88) kq[threadIdx.x] = (&K_KQ_TABLE[0][0])[threadIdx.x];
   __syncthreads();
   const int warp = threadIdx.x >> 5;
@@ -535,7 +535,18 @@ __global__ void __launch_bounds__(COOP12_THREADS, 1) k_coop12_run(int which, siz
   c.status = status;
   c.progress = progress;
   c.sets_per_step = 2;
-  coop_run_block12(c, warp / COOP_WARPS, xch_base + c.lane, coop_program(which), [] { __syncthreads(); });
+  coop_run_block12<SPLIT>(c, warp / COOP_WARPS, xch_base + c.lane, coop_program(which), [] { __syncthreads(); });
+}
+__global__ void __launch_bounds__(COOP12_THREADS, 1) k_coop12_run(int which, size_t n, size_t n_pad, const u4* __restrict__ lines,
+                                                                  u4* __restrict__ gslots, u4* __restrict__ fio, uint8_t* __restrict__ status,
+                                                                  const unsigned* progress) {
+  coop12_body<2>(which, n, n_pad, lines, gslots, fio, status, progress);
+}
+// eighteen warps: one per (coefficient, Karatsuba component)
+__global__ void __launch_bounds__(3 * COOP_THREADS, 1) k_coop18_run(int which, size_t n, size_t n_pad, const u4* __restrict__ lines,
+                                                                    u4* __restrict__ gslots, u4* __restrict__ fio, uint8_t* __restrict__ status,
+                                                                    const unsigned* progress) {
+  coop12_body<3>(which, n, n_pad, lines, gslots, fio, status, progress);
 }
 
 // ---- the same block-layout machine with FOUR 32-item groups in one 24-warp block (one block per SM).  Warp w of a block
@@ -1235,6 +1246,7 @@ struct bn254_ctx {
   size_t lines_lat_max = 0;            // largest launch that uses the small-batch producer (default 64 items per SM; BN254_LINES_LAT_MAX)
   bool lines_walk4 = true;             // BN254_LINES_WALK4=0: small batches use the one-thread-per-item latency producer (measurement)
   size_t piped_max_groups = 0;         // most groups of a pipelined verify (default: 3/4 of the SMs; BN254_PIPED_MAX_GROUPS)
+  bool coop18 = true;                  // BN254_COOP18=0: twelve-warp blocks instead of eighteen (one warp per coefficient and Karatsuba component)
   bool coop12 = true;                  // BN254_COOP12=0: six-warp blocks even when a group has an SM to itself (measurement)
   line_t* d_lines = nullptr;
   aff<fq>* d_comb_g1 = nullptr;   // (d + 1) * 16^w * G1 generator
@@ -1336,6 +1348,7 @@ int bn254_ctx_create(int device, bn254_ctx** out) {
   if ((e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
   if (const char* w = getenv("BN254_PIPELINE")) ctx->pipeline_small = w[0] != '0';
   if (const char* w = getenv("BN254_COOP12")) ctx->coop12 = w[0] != '0';
+  if (const char* w = getenv("BN254_COOP18")) ctx->coop18 = w[0] != '0';
   ctx->piped_max_groups = (size_t)(ctx->sm_count - ctx->sm_count / 4);
   if (const char* w = getenv("BN254_PIPED_MAX_GROUPS")) ctx->piped_max_groups = (size_t)atoll(w);
   if (ctx->piped_max_groups > (size_t)ctx->sm_count) ctx->piped_max_groups = (size_t)ctx->sm_count;
@@ -1370,6 +1383,9 @@ int bn254_ctx_create(int device, bn254_ctx** out) {
     return fail("cudaFuncSetAttribute(k_coop12_run)", e);
   // the pipelined pair (producer + machine) must be co-resident on every SM whichever of the two is dispatched first
   cudaFuncSetAttribute(k_coop12_run, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if ((e = cudaFuncSetAttribute(k_coop18_run, cudaFuncAttributeMaxDynamicSharedMemorySize, COOP12_SMEM_BYTES)) != cudaSuccess)
+    return fail("cudaFuncSetAttribute(k_coop18_run)", e);
+  cudaFuncSetAttribute(k_coop18_run, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaFuncSetAttribute(k_coop_run, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaFuncSetAttribute(k_verify_lines_lat, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if ((e = cudaFuncSetAttribute(k_verify_lines_walk4, cudaFuncAttributeMaxDynamicSharedMemorySize, WALK_SMEM_BYTES)) != cudaSuccess)
@@ -1594,7 +1610,7 @@ static int launch_coop_groups(bn254_ctx* ctx, int which, size_t n, size_t n_pad,
     const size_t i0 = g0 * COOP_LANES;
     // a group has an SM to itself: twelve warps per group (latency layout)
     if (cnt <= sms && ctx->coop12 && ctx->pairing_mode == 0) {
-      k_coop12_run<<<(unsigned)cnt, COOP12_THREADS, COOP12_SMEM_BYTES, ctx->stream>>>(which, n > i0 ? n - i0 : 0, n_pad, lines + i0,
+      (ctx->coop18 ? k_coop18_run : k_coop12_run)<<<(unsigned)cnt, ctx->coop18 ? 3 * COOP_THREADS : COOP12_THREADS, COOP12_SMEM_BYTES, ctx->stream>>>(which, n > i0 ? n - i0 : 0, n_pad, lines + i0,
                                                                                     gslots ? gslots + i0 : gslots, fio ? fio + i0 : fio,
                                                                                     status ? status + i0 : status, progress ? progress + i0 : progress);
       ctx->launches++;
@@ -2482,7 +2498,7 @@ static int finish_payloads_dev(bn254_ctx* ctx, const uint8_t* payloads, size_t m
   DALLOC(GSf, sizeof(u4) * COOP_GSLOTS * 6 * 2 * 2 * COOP_LANES);
   LAUNCH(k_finish_prepare, 1, BN_BLOCK, payloads, (int)m, agg_sig, ctx->d_lines, LNf.as<u4>(), FIOf.as<u4>(), status);
   if (ctx->coop12)
-    k_coop12_run<<<1, COOP12_THREADS, COOP12_SMEM_BYTES, ctx->stream>>>(CPROG_FINISH, (size_t)1, (size_t)COOP_LANES, LNf.as<u4>(), GSf.as<u4>(), FIOf.as<u4>(),
+    (ctx->coop18 ? k_coop18_run : k_coop12_run)<<<1, ctx->coop18 ? 3 * COOP_THREADS : COOP12_THREADS, COOP12_SMEM_BYTES, ctx->stream>>>(CPROG_FINISH, (size_t)1, (size_t)COOP_LANES, LNf.as<u4>(), GSf.as<u4>(), FIOf.as<u4>(),
                                                                         status, (const unsigned*)nullptr);
   else
     k_coop_run<<<1, COOP_THREADS, COOP1_SMEM_BYTES, ctx->stream>>>(CPROG_FINISH, (size_t)1, (size_t)COOP_LANES, LNf.as<u4>(), GSf.as<u4>(), FIOf.as<u4>(), status,

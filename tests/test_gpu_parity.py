@@ -1061,10 +1061,10 @@ def test_verify_with_cached_key_lines(E):
 @pytest.mark.parametrize("n", [1, 2, 31, 33, 111 * 32, 111 * 32 + 1, 148 * 32, 148 * 32 + 1])
 def test_small_batch_latency_path(E, n):
     """Small batches take the low-latency route (counter-parallel hash, the four-warp cooperative walk as the line producer on its
-    own stream, twelve-warp one-group blocks of the machine consuming the line sets WHILE they are produced): verdicts must be the
+    own stream, eighteen-warp one-group blocks of the machine consuming the line sets WHILE they are produced): verdicts must be the
     oracle's, with forged, undecodable and infinite items in the batch, under both input policies, and equal to the unpipelined
     route (BN254_PIPELINE=0).  On a 148-SM device 111 * 32 is the last batch that is pipelined, 148 * 32 the last whose groups get
-    twelve-warp blocks, 148 * 32 + 1 the first on six-warp blocks."""
+    eighteen-warp blocks, 148 * 32 + 1 the first on six-warp blocks."""
     from bn254_b200._native import Context
     msgs, sks, sigs, pks = _signed_set(E, n, seed=1000 + n)
     msgs, sigs, pks = bytearray(msgs), bytearray(sigs), bytearray(pks)
@@ -1098,14 +1098,22 @@ def test_small_batch_latency_path(E, n):
         legacy = Context(0)
     finally:
         del os.environ["BN254_LINES_WALK4"], os.environ["BN254_COOP12"]
+    os.environ["BN254_COOP18"] = "0"                                    # twelve-warp blocks instead of eighteen
+    try:
+        twelve = Context(0)
+    finally:
+        del os.environ["BN254_COOP18"]
     try:
         E.set_input_policy(E.INPUTS_TYPED, ctx=plain)
         assert E.verify_batch(msgs, 32, sigs, pks, ctx=plain) == want
         E.set_input_policy(E.INPUTS_TYPED, ctx=legacy)
         assert E.verify_batch(msgs, 32, sigs, pks, ctx=legacy) == want
+        E.set_input_policy(E.INPUTS_TYPED, ctx=twelve)
+        assert E.verify_batch(msgs, 32, sigs, pks, ctx=twelve) == want
         want_strict = bytes(_untrusted_expect(msgs[32 * i:32 * i + 32], sigs[64 * i:64 * i + 64], pks[128 * i:128 * i + 128]) for i in range(min(n, 64)))
         assert E.verify_batch(msgs, 32, sigs, pks, ctx=strict)[:len(want_strict)] == want_strict
     finally:
         strict.close()
         plain.close()
         legacy.close()
+        twelve.close()
