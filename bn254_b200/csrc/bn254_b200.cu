@@ -369,6 +369,12 @@ __global__ void __launch_bounds__(32) k_verify_lines_lat(const g1aff* __restrict
   }
 }
 
+// Fq2 routines of the cooperative walk: the compact by-value form.  (The form with three products in flight, which a LONE warp
+// needs, buys nothing here -- four warps already interleave, and behind the machine the walk is not the critical path: 2.54 ms per
+// one-item verify either way -- and as a producer of mid-size batches it is 25 % slower: 27.4 vs 21.8 ms per 2^18 items.)
+#ifndef BN_WALK_MUL
+#define BN_WALK_MUL lines_mul_call
+#endif
 // the producer of small batches: four warps walk the 32 items of a group together (coop_lines.cuh "cooperative walk"), one block per group
 __global__ void __launch_bounds__(WALK_WARPS * 32, 4) k_verify_lines_walk4(const g1aff* __restrict__ H, const uint8_t* __restrict__ sigs,
                                                                         const uint8_t* __restrict__ pks, size_t n, u4* __restrict__ lines, size_t n_pad,
@@ -410,9 +416,9 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, 4) k_verify_lines_walk4(const
   walk_schedule(
       [&](int kind, int level, size_t m, int sqx, int sqy) {
         if (kind == 0)
-          walk_dbl<lines_mul_ilp>(c, level, m);
+          walk_dbl<BN_WALK_MUL>(c, level, m);
         else
-          walk_add<lines_mul_ilp>(c, level, m, sqx, sqy);
+          walk_add<BN_WALK_MUL>(c, level, m, sqx, sqy);
       },
       [] { __syncthreads(); },
       [&](size_t m) {  // every store of steps < m is before the barrier this thread has just left: fence, then publish
@@ -1243,9 +1249,10 @@ struct bn254_ctx {
   cudaStream_t aux_stream = nullptr;   // small-batch verify: the line producer runs here WHILE the machine consumes its line sets
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool pipeline_small = true;          // BN254_PIPELINE=0 turns the producer / machine overlap off (measurement)
-  size_t lines_lat_max = 0;            // largest launch that uses the small-batch producer (default 64 items per SM; BN254_LINES_LAT_MAX)
+  size_t lines_lat_max = 0;            // largest launch that uses the small-batch producer (default 160 items per SM; BN254_LINES_LAT_MAX)
   bool lines_walk4 = true;             // BN254_LINES_WALK4=0: small batches use the one-thread-per-item latency producer (measurement)
   size_t piped_max_groups = 0;         // most groups of a pipelined verify (default: 3/4 of the SMs; BN254_PIPED_MAX_GROUPS)
+  bool coop_tail_split = true;         // BN254_COOP_TAIL_SPLIT=0: the remainder of a launch of a few waves runs as four-group blocks too (measurement)
   bool coop18 = true;                  // BN254_COOP18=0: twelve-warp blocks instead of eighteen (one warp per coefficient and Karatsuba component)
   bool coop12 = true;                  // BN254_COOP12=0: six-warp blocks even when a group has an SM to itself (measurement)
   line_t* d_lines = nullptr;
@@ -1349,11 +1356,12 @@ int bn254_ctx_create(int device, bn254_ctx** out) {
   if (const char* w = getenv("BN254_PIPELINE")) ctx->pipeline_small = w[0] != '0';
   if (const char* w = getenv("BN254_COOP12")) ctx->coop12 = w[0] != '0';
   if (const char* w = getenv("BN254_COOP18")) ctx->coop18 = w[0] != '0';
+  if (const char* w = getenv("BN254_COOP_TAIL_SPLIT")) ctx->coop_tail_split = w[0] != '0';
   ctx->piped_max_groups = (size_t)(ctx->sm_count - ctx->sm_count / 4);
   if (const char* w = getenv("BN254_PIPED_MAX_GROUPS")) ctx->piped_max_groups = (size_t)atoll(w);
   if (ctx->piped_max_groups > (size_t)ctx->sm_count) ctx->piped_max_groups = (size_t)ctx->sm_count;
   if (const char* w = getenv("BN254_LINES_WALK4")) ctx->lines_walk4 = w[0] != '0';
-  ctx->lines_lat_max = (size_t)ctx->sm_count * 64;
+  ctx->lines_lat_max = (size_t)ctx->sm_count * 160;
   if (const char* w = getenv("BN254_LINES_LAT_MAX")) ctx->lines_lat_max = (size_t)atoll(w);
   if ((e = cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
   // A private pool (the device's default pool is shared with the host process, e.g. torch): freed blocks stay cached here
@@ -1633,6 +1641,20 @@ static int launch_coop_groups(bn254_ctx* ctx, int which, size_t n, size_t n_pad,
   // plus a one-group tail was measured too: +5 %, the tail blocks run two deep.)
   if (groups <= 2 * sms) {
     one_group_blocks(0, groups);
+    CK(cudaGetLastError());
+    return 0;
+  }
+  // Launches of a few waves: a remainder of at most two groups per SM behind the last whole wave of four-group blocks runs as
+  // one-group blocks (eighteen warps when it is at most one group per SM) instead of a mostly empty wave of its own: a wave costs
+  // 6.6 ms, the one-group blocks 2.3 ms (one per SM) or 4.7 ms (two per SM).  Only up to eight whole waves -- for big launches
+  // the split was measured slower (r02 tuning log, v6) and the remainder is under a few per cent of the time anyway.
+  const size_t wave = COOP4_GROUPS * sms, whole = groups / wave, rest = groups % wave;
+  if (ctx->coop_tail_split && whole >= 1 && whole <= 8 && rest > 0 && rest <= 2 * sms) {
+    const size_t main_groups = whole * wave, main_items = main_groups * COOP_LANES;
+    k_coop4_run<<<(unsigned)(main_groups / COOP4_GROUPS), COOP4_THREADS, COOP4_SMEM_BYTES, ctx->stream>>>(which, n < main_items ? n : main_items, n_pad, lines,
+                                                                                                        gslots, fio, status, ctx->coop_stagger);
+    ctx->launches++;
+    one_group_blocks(main_groups, rest);
     CK(cudaGetLastError());
     return 0;
   }

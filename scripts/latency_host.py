@@ -16,7 +16,7 @@ from bn254_b200 import engine as E
 def main():
     ctx = E.context(0)
     E.set_input_policy(E.INPUTS_TYPED, ctx=ctx)
-    n = 1 << 13
+    n = 1 << 15
     msgs, sks = synth.messages(n, 32, seed=1), synth.secret_keys(n, seed=2)
     sigs, st = E.sign_batch(msgs, 32, sks, ctx=ctx)
     pks = E.derive_pk_g2_batch(sks, ctx=ctx)

@@ -1058,6 +1058,43 @@ def test_verify_with_cached_key_lines(E):
         strict.close()
 
 
+@pytest.mark.parametrize("groups", [2 * 148 + 1, 4 * 148 + 1, 4 * 148 + 148, 4 * 148 + 149, 4 * 148 + 2 * 148 + 1])
+def test_mid_size_launch_shapes(E, groups):
+    """Batches of one to two waves of the machine: the cooperative walk as the producer (up to 160 items per SM), four-group
+    blocks for the whole waves and one-group blocks (eighteen warps / six warps) for a short remainder.  Verdicts = the oracle's,
+    with forged, undecodable and infinite items placed in the first block, at the wave boundary and in the remainder; and the same
+    bytes with the remainder split off (BN254_COOP_TAIL_SPLIT=0)."""
+    from bn254_b200._native import Context
+    n = groups * 32 - 5
+    msgs, sks, sigs, pks = _signed_set(E, n, seed=4000 + groups)
+    msgs, sigs, pks = bytearray(msgs), bytearray(sigs), bytearray(pks)
+    spots = [0, 31, 32, 4 * 148 * 32 - 1, 4 * 148 * 32, 4 * 148 * 32 + 33, n - 40, n - 1]
+    for t, i in enumerate(i for i in spots if 0 <= i < n):
+        kind = t % 4
+        if kind == 0:
+            msgs[32 * i + 1] ^= 0x40
+        elif kind == 1:
+            sigs[64 * i:64 * i + 64] = O.g1_neg(bytes(sigs[64 * i:64 * i + 64]))[1]
+        elif kind == 2:
+            sigs[64 * i + 63] ^= 1
+        else:
+            pks[128 * i:128 * i + 128] = bytes(128)
+    msgs, sigs, pks = bytes(msgs), bytes(sigs), bytes(pks)
+    want = O.verify_batch(msgs, 32, sigs, pks, n, NTHREADS)
+    assert sum(1 for b in want if b) >= 4
+    assert E.verify_batch(msgs, 32, sigs, pks) == want
+    os.environ["BN254_COOP_TAIL_SPLIT"] = "0"
+    try:
+        whole = Context(0)
+    finally:
+        del os.environ["BN254_COOP_TAIL_SPLIT"]
+    try:
+        E.set_input_policy(E.INPUTS_TYPED, ctx=whole)
+        assert E.verify_batch(msgs, 32, sigs, pks, ctx=whole) == want
+    finally:
+        whole.close()
+
+
 @pytest.mark.parametrize("n", [1, 2, 31, 33, 111 * 32, 111 * 32 + 1, 148 * 32, 148 * 32 + 1])
 def test_small_batch_latency_path(E, n):
     """Small batches take the low-latency route (counter-parallel hash, the four-warp cooperative walk as the line producer on its
