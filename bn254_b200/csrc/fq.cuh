@@ -311,6 +311,66 @@ BN_FN fq fq_reduce9(const uint32_t (&t)[9], const uint32_t* kq) {
 #endif
   return fq_csub(r);
 }
+// t = a + K - b on nine limbs, for a, b < 2^256 and a constant K (a multiple of q, eight limbs) with a + K >= b.  No reduction.
+BN_FN void fq9_addk_sub(uint32_t (&t)[9], const fq& a, const uint32_t (&K)[8], const fq& b) {
+#if defined(__CUDA_ARCH__)
+  asm("add.cc.u32 %0, %9, %17;\n\t"
+      "addc.cc.u32 %1, %10, %18;\n\t"
+      "addc.cc.u32 %2, %11, %19;\n\t"
+      "addc.cc.u32 %3, %12, %20;\n\t"
+      "addc.cc.u32 %4, %13, %21;\n\t"
+      "addc.cc.u32 %5, %14, %22;\n\t"
+      "addc.cc.u32 %6, %15, %23;\n\t"
+      "addc.cc.u32 %7, %16, %24;\n\t"
+      "addc.u32 %8, 0, 0;\n\t"
+      : "=&r"(t[0]), "=&r"(t[1]), "=&r"(t[2]), "=&r"(t[3]), "=&r"(t[4]), "=&r"(t[5]), "=&r"(t[6]), "=&r"(t[7]), "=&r"(t[8])
+      : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]), "r"(K[0]), "r"(K[1]), "r"(K[2]),
+        "r"(K[3]), "r"(K[4]), "r"(K[5]), "r"(K[6]), "r"(K[7]));
+  asm("sub.cc.u32 %0, %0, %9;\n\t"
+      "subc.cc.u32 %1, %1, %10;\n\t"
+      "subc.cc.u32 %2, %2, %11;\n\t"
+      "subc.cc.u32 %3, %3, %12;\n\t"
+      "subc.cc.u32 %4, %4, %13;\n\t"
+      "subc.cc.u32 %5, %5, %14;\n\t"
+      "subc.cc.u32 %6, %6, %15;\n\t"
+      "subc.cc.u32 %7, %7, %16;\n\t"
+      "subc.u32 %8, %8, 0;\n\t"
+      : "+r"(t[0]), "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]), "+r"(t[8])
+      : "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
+#else
+  int64_t c = 0;
+  for (int i = 0; i < 9; i++) {
+    c += (int64_t)(i < 8 ? a.l[i] : 0) + (int64_t)(i < 8 ? K[i] : 0) - (int64_t)(i < 8 ? b.l[i] : 0);
+    t[i] = (uint32_t)c;
+    c >>= 32;  // arithmetic shift: borrow / carry in one
+  }
+#endif
+}
+// a + b as a 256-bit number (no reduction; the caller knows it fits)
+BN_FN fq fq_add_raw(const fq& a, const fq& b) {
+  fq s;
+#if defined(__CUDA_ARCH__)
+  asm("add.cc.u32 %0, %8, %16;\n\t"
+      "addc.cc.u32 %1, %9, %17;\n\t"
+      "addc.cc.u32 %2, %10, %18;\n\t"
+      "addc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\t"
+      "addc.cc.u32 %5, %13, %21;\n\t"
+      "addc.cc.u32 %6, %14, %22;\n\t"
+      "addc.u32 %7, %15, %23;\n\t"
+      : "=&r"(s.l[0]), "=&r"(s.l[1]), "=&r"(s.l[2]), "=&r"(s.l[3]), "=&r"(s.l[4]), "=&r"(s.l[5]), "=&r"(s.l[6]), "=&r"(s.l[7])
+      : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]),
+        "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
+#else
+  uint64_t c = 0;
+  for (int i = 0; i < 8; i++) {
+    c += (uint64_t)a.l[i] + b.l[i];
+    s.l[i] = (uint32_t)c;
+    c >>= 32;
+  }
+#endif
+  return s;
+}
 // (9 x + z) mod q in one reduction, for x < q and z <= q (canonical, or q itself): t = 9 x + z < 10 q is formed on nine
 // limbs, the quotient k = floor(t / q) is estimated from the top 32 bits of t >> 226 (reciprocal multiplication; the
 // estimate is k or k - 1, checked exhaustively at the multiples of q and on 3 * 10^5 random values in the tests), k q comes

@@ -267,7 +267,7 @@ struct coop_sim {
               coop_line_fetch(c, line_next[k][l], line_next[k][l] & 1);
               line_next[k][l]++;
             }
-            t[k * COOP_LANES + l] = coop_dot_block_any(c.sm, plan, k);
+            t[k * COOP_LANES + l] = coop_dot_block_any(c.sm, plan, k, c.kq);
           }
         for (int l = 0; l < lanes; l++)
           for (int k = 0; k < COOP_WARPS; k++) {
