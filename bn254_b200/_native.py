@@ -9,7 +9,7 @@ LIB_PATH = os.environ.get("BN254_B200_LIB") or os.path.join(HERE, "libbn254_b200
 # every symbol include/bn254_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "bn254_ctx_create", "bn254_ctx_destroy", "bn254_last_error", "bn254_sync", "bn254_stream", "bn254_sm_count", "bn254_launch_count",
-    "bn254_set_profiling", "bn254_phase_ms", "bn254_set_pairing_mode", "bn254_trim", "bn254_set_input_policy", "bn254_get_input_policy", "bn254_set_hash_try_limit",
+    "bn254_set_profiling", "bn254_phase_ms", "bn254_set_pairing_mode", "bn254_trim", "bn254_set_input_policy", "bn254_get_input_policy", "bn254_set_hash_try_limit", "bn254_set_test_fault",
     "bn254_hash_to_g1_batch", "bn254_hash_to_g1_batch_dev", "bn254_hash_to_g1_var",
     "bn254_sign_batch", "bn254_sign_batch_dev", "bn254_verify_batch", "bn254_verify_batch_dev",
     "bn254_verify_batch_rlc", "bn254_verify_batch_rlc_dev",

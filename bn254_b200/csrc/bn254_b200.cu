@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(32) k_verify_lines_lat(const g1aff* __restrict
 __global__ void __launch_bounds__(WALK_WARPS * 32, 4) k_verify_lines_walk4(const g1aff* __restrict__ H, const uint8_t* __restrict__ sigs,
                                                                         const uint8_t* __restrict__ pks, size_t n, u4* __restrict__ lines, size_t n_pad,
                                                                         uint8_t* __restrict__ status, const line_t* __restrict__ table,
-                                                                        unsigned* __restrict__ progress) {
+                                                                        unsigned* __restrict__ progress, size_t mute_item) {
   extern __shared__ u4 walk_sm[];
   walk_ctx c;
   c.lane = threadIdx.x & 31;
@@ -405,6 +405,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, 4) k_verify_lines_walk4(const
   walk_decode(c, &h, sigs + 64 * c.item, pks + 128 * c.item, skip);
   __syncthreads();
   const int st = walk_flags(c, skip);
+  if (c.item == mute_item) progress = nullptr;  // test hook (bn254_set_test_fault): this item's progress is never published
   const bool reporter = c.warp == WALK_WARPS - 1 && c.item < n;  // the warp with the shortest first level reports for the group
   if (reporter && !c.live) {  // no line set will be written: the status is final, do not keep a pipelined machine waiting
     if (!skip) status[c.item] = (uint8_t)st;
@@ -1253,6 +1254,8 @@ struct bn254_ctx {
   bool lines_walk4 = true;             // BN254_LINES_WALK4=0: small batches use the one-thread-per-item latency producer (measurement)
   size_t piped_max_groups = 0;         // most groups of a pipelined verify (default: 3/4 of the SMs; BN254_PIPED_MAX_GROUPS)
   bool coop_tail_split = true;         // BN254_COOP_TAIL_SPLIT=0: the remainder of a launch of a few waves runs as four-group blocks too (measurement)
+  size_t test_mute_item = ~(size_t)0;  // bn254_set_test_fault: the pipelined producer never publishes this item (exercises BN254_ENGINE_FAULT)
+  unsigned fault_retries = 0;          // host-buffer calls that found a BN254_ENGINE_FAULT status and ran again without pipelining
   bool coop18 = true;                  // BN254_COOP18=0: twelve-warp blocks instead of eighteen (one warp per coefficient and Karatsuba component)
   bool coop12 = true;                  // BN254_COOP12=0: six-warp blocks even when a group has an SM to itself (measurement)
   line_t* d_lines = nullptr;
@@ -1743,7 +1746,7 @@ static int verify_dev_impl(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, 
         CK(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
         if (ctx->lines_walk4)
           k_verify_lines_walk4<<<(unsigned)(m_pad / COOP_LANES), WALK_WARPS * 32, WALK_SMEM_BYTES, ctx->aux_stream>>>(
-              h, sigs + 64 * off, pks + 128 * off, m, LN.as<u4>(), m_pad, status + off, ctx->d_lines, PR.as<unsigned>());
+              h, sigs + 64 * off, pks + 128 * off, m, LN.as<u4>(), m_pad, status + off, ctx->d_lines, PR.as<unsigned>(), ctx->test_mute_item);
         else
           k_verify_lines_lat<<<grid_for(m, 32), 32, 0, ctx->aux_stream>>>(h, sigs + 64 * off, pks + 128 * off, m, LN.as<u4>(), m_pad, status + off,
                                                                           ctx->d_lines, PR.as<unsigned>());
@@ -1760,7 +1763,7 @@ static int verify_dev_impl(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, 
       }
       if (lat && ctx->lines_walk4) {
         k_verify_lines_walk4<<<(unsigned)(m_pad / COOP_LANES), WALK_WARPS * 32, WALK_SMEM_BYTES, ctx->stream>>>(
-            h, sigs + 64 * off, pks + 128 * off, m, LN.as<u4>(), m_pad, status + off, ctx->d_lines, (unsigned*)nullptr);
+            h, sigs + 64 * off, pks + 128 * off, m, LN.as<u4>(), m_pad, status + off, ctx->d_lines, (unsigned*)nullptr, ~(size_t)0);
         ctx->launches++;
         CK(cudaGetLastError());
       } else if (lat)
@@ -1901,6 +1904,17 @@ int bn254_verify_batch_dev(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, 
   ARGCHECK(msgs != nullptr);
   return verify_dev_impl(ctx, msgs, msg_len, sigs, pks, n, status);
 }
+// a host-side status array of a batch small enough to have been pipelined holds BN254_ENGINE_FAULT
+static bool faulted(const bn254_ctx* ctx, const uint8_t* status, size_t n) {
+  return ctx->pipeline_small && n <= ctx->piped_max_groups * COOP_LANES && memchr(status, ST_ENGINE_FAULT, n) != nullptr;
+}
+// test hook: the pipelined line producer never publishes item `item` (~0 = off); *retries = host-buffer calls that ran again
+int bn254_set_test_fault(bn254_ctx* ctx, size_t item, uint32_t* retries) {
+  ENTER();
+  ctx->test_mute_item = item;
+  if (retries) *retries = ctx->fault_retries;
+  return 0;
+}
 int bn254_verify_batch(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, const uint8_t* sigs, const uint8_t* pks, size_t n,
                        uint8_t* status) {
   ENTER();
@@ -1925,6 +1939,16 @@ int bn254_verify_batch(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, cons
     if (rc) return rc;
     D2H(status, d_st.p, n);
     CK(cudaStreamSynchronize(ctx->stream));
+    if (faulted(ctx, status, n)) {  // never observed outside the test hook: run again, producer and machine one after the other
+      const bool keep = ctx->pipeline_small;
+      ctx->pipeline_small = false;
+      ctx->fault_retries++;
+      rc = verify_dev_impl(ctx, d_msgs.as<uint8_t>(), msg_len, d_sigs.as<uint8_t>(), d_pks.as<uint8_t>(), n, d_st.as<uint8_t>());
+      ctx->pipeline_small = keep;
+      if (rc) return rc;
+      D2H(status, d_st.p, n);
+      CK(cudaStreamSynchronize(ctx->stream));
+    }
     return 0;
   };
   int rc = body();
@@ -1948,6 +1972,17 @@ int bn254_check_public_keys_batch(bn254_ctx* ctx, const uint8_t* pk_g2, const ui
   if (rc) return rc;
   D2H(status, d_st.p, n);
   CK(cudaStreamSynchronize(ctx->stream));
+  if (faulted(ctx, status, n)) {
+    const bool keep = ctx->pipeline_small;
+    ctx->pipeline_small = false;
+    ctx->fault_retries++;
+    cudaError_t e = cudaMemsetAsync(d_st.p, 0, n, ctx->stream);
+    rc = e == cudaSuccess ? verify_dev_impl(ctx, nullptr, 0, d_g1.as<uint8_t>(), d_g2.as<uint8_t>(), n, d_st.as<uint8_t>()) : BN254_E_CUDA;
+    ctx->pipeline_small = keep;
+    if (rc) return rc;
+    D2H(status, d_st.p, n);
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
   return 0;
 }
 

@@ -90,6 +90,11 @@ int bn254_get_input_policy(bn254_ctx* ctx);
 /* test hook: number of counters hash_to_try_and_increment tries (255 in the reference, /root/reference/src/hash.rs:39); lowering
  * it is the only way to reach HashToPointError (/root/reference/src/hash.rs:62), whose natural probability is 2^-235 */
 int bn254_set_hash_try_limit(bn254_ctx* ctx, int max_tries);
+/* test hook for BN254_ENGINE_FAULT: the line producer of a pipelined small-batch verify never publishes item `item` ((size_t)-1 =
+ * off), so the machine's bounded wait for it times out (~1 s) and the item gets status 255.  The host-buffer entry points
+ * (bn254_verify_batch, bn254_check_public_keys_batch) then run the batch again without pipelining and return real statuses;
+ * *retries (may be NULL) = how many calls on this context did that.  The _dev entry points leave the 255 for the caller. */
+int bn254_set_test_fault(bn254_ctx* ctx, size_t item, uint32_t* retries);
 
 /* measurement support: when on, the verify pipeline brackets its three kernels (hash, Miller loop, final
  * exponentiation) with CUDA events on the context's stream; bn254_phase_ms returns and clears the accumulated times */

@@ -1058,6 +1058,43 @@ def test_verify_with_cached_key_lines(E):
         strict.close()
 
 
+def test_engine_fault_is_reported_and_retried(E):
+    """The bounded producer / machine handshake of the pipelined small-batch verify: with the test hook the producer never
+    publishes item 5, the machine's wait for it times out, and (a) the device-resident entry point reports status 255
+    (BN254_ENGINE_FAULT) for that item and real verdicts for all others, (b) the host-buffer entry point notices the 255, runs the
+    batch again without pipelining and returns the oracle's statuses."""
+    import ctypes
+    import torch
+    from bn254_b200._native import Context, S
+    n = 40
+    msgs, sks, sigs, pks = _signed_set(E, n, seed=77)
+    bad = bytearray(sigs)
+    bad[64 * 9:64 * 10] = O.g1_neg(bytes(sigs[64 * 9:64 * 10]))[1]
+    bad = bytes(bad)
+    want = O.verify_batch(msgs, 32, bad, pks, n, NTHREADS)
+    assert want[9] == 9 and sum(1 for b in want if b) == 1
+    ctx = Context(0)
+    try:
+        E.set_input_policy(E.INPUTS_TYPED, ctx=ctx)
+        retries = ctypes.c_uint32(0)
+        ctx.call("bn254_set_test_fault", S(5), retries)
+        assert retries.value == 0
+        dev = lambda b: torch.frombuffer(bytearray(b), dtype=torch.uint8).cuda()
+        d_st = torch.zeros(n, dtype=torch.uint8, device="cuda")
+        ctx.call("bn254_verify_batch_dev", dev(msgs), S(32), dev(bad), dev(pks), S(n), d_st)
+        ctx.sync()
+        got = bytes(d_st.cpu().numpy().tobytes())
+        assert got[5] == 255 and got[:5] + got[6:] == want[:5] + want[6:]
+        assert E.verify_batch(msgs, 32, bad, pks, ctx=ctx) == want
+        ctx.call("bn254_set_test_fault", S(2 ** 64 - 1), retries)
+        assert retries.value == 1
+        assert E.verify_batch(msgs, 32, bad, pks, ctx=ctx) == want
+        ctx.call("bn254_set_test_fault", S(2 ** 64 - 1), retries)
+        assert retries.value == 1
+    finally:
+        ctx.close()
+
+
 @pytest.mark.parametrize("groups", [2 * 148 + 1, 4 * 148 + 1, 4 * 148 + 148, 4 * 148 + 149, 4 * 148 + 2 * 148 + 1])
 def test_mid_size_launch_shapes(E, groups):
     """Batches of one to two waves of the machine: the cooperative walk as the producer (up to 160 items per SM), four-group
