@@ -94,29 +94,35 @@ __global__ void __launch_bounds__(BN_BLOCK) k_hash_round(const uint8_t* __restri
     }
   }
 }
-// ---- counter-parallel hash: one WARP per message, lane l tries counter base + l, the lowest accepted counter wins (exactly the
-// point the sequential loop returns).  32 x the work of the loop per step, but one step (0.2 ms) almost always decides: used for
-// small batches, where the loop's latency is the slowest lane's try count, and for the survivors of the compacting rounds.
+// ---- counter-parallel hash: G lanes per message (G = 32, 8, 4, 2), lane j of a group tries counter base + j, the lowest accepted
+// counter wins (exactly the point the sequential loop returns), groups that found nothing go on with the next G counters.  G x the
+// work of the loop per step, but one step (0.2 ms: the 254 dependent squarings of the square root) almost always decides.  Used for
+// small and mid-size batches, where the loop's latency is the slowest lane's try count -- G is chosen so that a step's G n tries
+// fit the ~28 k tries the GPU completes in the latency of one -- and (G = 32) for the survivors of the compacting rounds.
 // list_in == NULL: items 0 .. n-1; else items list_in[0 .. *count_in).
+template <int G>
 __global__ void __launch_bounds__(BN_BLOCK) k_hash_wide(const uint8_t* __restrict__ msgs, size_t msg_len, const uint64_t* __restrict__ offsets,
                                                         size_t n, const uint32_t* __restrict__ list_in, const uint32_t* __restrict__ count_in,
                                                         int ctr0, int max_tries, g1aff* __restrict__ H, uint8_t* __restrict__ status,
                                                         uint8_t* __restrict__ tries) {
   const size_t total = list_in ? (size_t)*count_in : n;
-  const unsigned lane = threadIdx.x & 31;
-  const size_t warps = ((size_t)gridDim.x * blockDim.x) >> 5;
-  for (size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total; w += warps) {
-    const size_t i = list_in ? list_in[w] : w;
+  const unsigned lane = threadIdx.x & 31, sub = lane % G, grp = lane / G;
+  const unsigned gmask = G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u) << (grp * G);
+  const size_t per_warp = 32 / G, warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  for (size_t wb = (((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * per_warp; wb < total; wb += warps * per_warp) {
+    const size_t w = wb + grp;
+    const bool valid = w < total;
+    const size_t i = valid ? (list_in ? list_in[w] : w) : 0;
     const uint8_t* m = offsets ? msgs + offsets[i] : msgs + i * msg_len;
     const uint64_t len = offsets ? offsets[i + 1] - offsets[i] : msg_len;
-    bool done = false;
-    for (int base = ctr0; base < max_tries && !done; base += 32) {
-      const int ctr = base + (int)lane;
+    bool done = !valid;
+    for (int base = ctr0; base < max_tries && __any_sync(0xffffffffu, !done); base += G) {
+      const int ctr = base + (int)sub;
       g1aff h;
       bool ok = false;
-      if (ctr < max_tries) ok = hash_to_g1(&h.x, &h.y, m, len, nullptr, ctr + 1, ctr) == ST_OK;
-      const unsigned hit = __ballot_sync(0xffffffffu, ok);
-      if (hit) {
+      if (!done && ctr < max_tries) ok = hash_to_g1(&h.x, &h.y, m, len, nullptr, ctr + 1, ctr) == ST_OK;
+      const unsigned hit = __ballot_sync(0xffffffffu, ok) & gmask;
+      if (!done && hit) {
         if (lane == (unsigned)(__ffs(hit) - 1)) {
           H[i] = h;
           status[i] = ST_OK;
@@ -125,7 +131,7 @@ __global__ void __launch_bounds__(BN_BLOCK) k_hash_wide(const uint8_t* __restric
         done = true;
       }
     }
-    if (!done && lane == 0) {
+    if (!done && sub == 0) {
       g1aff z;
       z.x = fq_zero();
       z.y = fq_zero();
@@ -1256,6 +1262,7 @@ struct bn254_ctx {
   bool coop_tail_split = true;         // BN254_COOP_TAIL_SPLIT=0: the remainder of a launch of a few waves runs as four-group blocks too (measurement)
   size_t test_mute_item = ~(size_t)0;  // bn254_set_test_fault: the pipelined producer never publishes this item (exercises BN254_ENGINE_FAULT)
   unsigned fault_retries = 0;          // host-buffer calls that found a BN254_ENGINE_FAULT status and ran again without pipelining
+  bool hash_groups = true;             // BN254_HASH_GROUPS=0: the counter-parallel hash always uses 32 lanes per message, up to 8192 messages (measurement)
   bool coop18 = true;                  // BN254_COOP18=0: twelve-warp blocks instead of eighteen (one warp per coefficient and Karatsuba component)
   bool coop12 = true;                  // BN254_COOP12=0: six-warp blocks even when a group has an SM to itself (measurement)
   line_t* d_lines = nullptr;
@@ -1359,6 +1366,7 @@ int bn254_ctx_create(int device, bn254_ctx** out) {
   if (const char* w = getenv("BN254_PIPELINE")) ctx->pipeline_small = w[0] != '0';
   if (const char* w = getenv("BN254_COOP12")) ctx->coop12 = w[0] != '0';
   if (const char* w = getenv("BN254_COOP18")) ctx->coop18 = w[0] != '0';
+  if (const char* w = getenv("BN254_HASH_GROUPS")) ctx->hash_groups = w[0] != '0';
   if (const char* w = getenv("BN254_COOP_TAIL_SPLIT")) ctx->coop_tail_split = w[0] != '0';
   ctx->piped_max_groups = (size_t)(ctx->sm_count - ctx->sm_count / 4);
   if (const char* w = getenv("BN254_PIPED_MAX_GROUPS")) ctx->piped_max_groups = (size_t)atoll(w);
@@ -1494,15 +1502,25 @@ uint64_t bn254_launch_count(bn254_ctx* ctx) { return ctx ? ctx->launches : 0; }
 #ifndef BN_HASH_ROUNDS
 #define BN_HASH_ROUNDS 10
 #endif
-#define BN_HASH_WIDE_MAX 8192
+#define BN_HASH_WIDE_MAX (ctx->hash_groups ? 32768u : 8192u)
 static int hash_dev(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, const uint64_t* offsets, size_t n, g1aff* H, uint8_t* status,
                     uint8_t* tries) {
   if (n == 0) return 0;
   const int cap = ctx->hash_try_limit;
   // small batches: one warp per message, 32 counters at a time (latency of ONE try instead of the unluckiest lane's count)
   if (n <= BN_HASH_WIDE_MAX) {
-    LAUNCH(k_hash_wide, grid_for(n * 32), BN_BLOCK, msgs, msg_len, offsets, n, (const uint32_t*)nullptr, (const uint32_t*)nullptr, 0, cap, H, status,
-           tries);
+#define HASH_WIDE(G) \
+  LAUNCH(k_hash_wide<G>, grid_for(n * G), BN_BLOCK, msgs, msg_len, offsets, n, (const uint32_t*)nullptr, (const uint32_t*)nullptr, 0, cap, H, status, tries)
+    if (n <= 1024 || !ctx->hash_groups) {
+      HASH_WIDE(32);
+    } else if (n <= 4096) {
+      HASH_WIDE(8);
+    } else if (n <= 16384) {
+      HASH_WIDE(4);
+    } else {
+      HASH_WIDE(2);
+    }
+#undef HASH_WIDE
     return 0;
   }
   // big batches of ragged / multi-block messages, and callers that want the counters: one thread loops per item
@@ -1529,7 +1547,7 @@ static int hash_dev(bn254_ctx* ctx, const uint8_t* msgs, size_t msg_len, const u
   }
   size_t warps = (size_t)(expect * 1.25) + 4096;
   if (warps > n) warps = n;
-  LAUNCH(k_hash_wide, grid_for(warps * 32), BN_BLOCK, msgs, msg_len, (const uint64_t*)nullptr, n, L[(rounds - 1) & 1], C + rounds, rounds, cap, H, status,
+  LAUNCH(k_hash_wide<32>, grid_for(warps * 32), BN_BLOCK, msgs, msg_len, (const uint64_t*)nullptr, n, L[(rounds - 1) & 1], C + rounds, rounds, cap, H, status,
          (uint8_t*)nullptr);
   return 0;
 }
