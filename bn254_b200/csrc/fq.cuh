@@ -656,7 +656,14 @@ BN_FN fq fq_mul_ptx(const fq& a, const fq& b) {
 // structs use the register ABI, no stack traffic), and the pairing kernels' instruction footprint drops from
 // ~200 KB to a size the instruction cache holds -- with the product inlined at every use, two resident blocks
 // per SM spent more issue slots waiting for instruction fetch than on anything else (profiles/r01_*).
+#if defined(BN_FQ_MUL_WIDE)
+// the product through the 512-bit lazy accumulator of the cooperative machine (coop_mac.cuh: wide_mac + wide_redc + one conditional
+// subtraction), defined there -- same canonical result, different instruction mix (A/B, r02 tuning log)
+BN_FN fq fq_mul_wide(const fq& a, const fq& b);
+__device__ __noinline__ fq fq_mul_call(fq a, fq b) { return fq_mul_wide(a, b); }
+#else
 __device__ __noinline__ fq fq_mul_call(fq a, fq b) { return fq_mul_ptx(a, b); }
+#endif
 BN_FN fq fq_mul(const fq& a, const fq& b) { return fq_mul_call(a, b); }
 #else
 BN_FN fq fq_mul(const fq& a, const fq& b) { return fq_mul_ptx(a, b); }

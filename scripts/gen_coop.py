@@ -183,7 +183,11 @@ BN_FN fq wide_redc(uint64_t (&E)[8], uint64_t (&O)[8], uint32_t (&C)[8]) {
   return r;
 }
 """)
-    o.append("#endif\n\n}  // namespace bn\n")
+    o.append("#endif\n\n")
+    o.append("// one Montgomery product through the accumulator (fq.cuh BN_FQ_MUL_WIDE): T = a b < q^2, REDC leaves less than 1.19 q\n")
+    o.append("BN_FN fq fq_mul_wide(const fq& a, const fq& b) {\n  uint64_t E[8], O[8];\n  uint32_t C[8];\n")
+    o.append("#if defined(__CUDA_ARCH__)\n#pragma unroll\n#endif\n  for (int i = 0; i < 8; i++) {\n    E[i] = 0;\n    O[i] = 0;\n    C[i] = 0;\n  }\n")
+    o.append("  wide_mac(E, O, C, a.l, b.l);\n  return fq_csub(wide_redc(E, O, C));\n}\n\n}  // namespace bn\n")
     return "".join(o)
 
 
