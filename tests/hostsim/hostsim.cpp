@@ -380,6 +380,37 @@ API int hs_coop_verify_walk4(const uint8_t* msg, size_t len, const uint8_t* sig,
   S.run(K_COOP_PROG_VERIFY);
   return S.status;
 }
+// The latency layouts of the machine (coop.cuh coop_run_block12<SPLIT>: twelve / eighteen warps per group, the Karatsuba components
+// of a row on different warps, handed over through exchange slots): every simulated warp is a host THREAD running the device
+// function itself, the block barrier is a std::barrier.  One item (lane 0); the line sets come from the cooperative walk.
+#include <barrier>
+#include <thread>
+template <int SPLIT>
+static int coop_split_verify(const uint8_t* msg, size_t len, const uint8_t* sig, const uint8_t* pk) {
+  g1aff h;
+  int st = hash_to_g1(&h.x, &h.y, msg, len, nullptr);
+  if (st) return st;
+  coop_sim S;
+  st = walk4_sim(S.lines, S.n_pad, 1, &h, sig, pk);
+  if (st) return st;
+  std::vector<u4> xch(12 * 2 * COOP_LANES);
+  const int nw = SPLIT * COOP_WARPS;
+  std::barrier<> bar(nw);
+  std::vector<std::thread> th;
+  for (int w = 0; w < nw; w++)
+    th.emplace_back([&, w] {
+      coop_ctx c = S.ctx(w % COOP_WARPS, 0);
+      c.sets_per_step = 2;
+      coop_run_block12<SPLIT>(c, w / COOP_WARPS, xch.data(), K_COOP_PROG_VERIFY, [&] { bar.arrive_and_wait(); });
+    });
+  for (auto& t : th) t.join();
+  return S.status;
+}
+API int hs_coop_verify_split(const uint8_t* msg, size_t len, const uint8_t* sig, const uint8_t* pk, int split) {
+  ensure_init();
+  if (g_coop_wmode != 0) return -1;
+  return split == 3 ? coop_split_verify<3>(msg, len, sig, pk) : coop_split_verify<2>(msg, len, sig, pk);
+}
 // Miller product of the verify pairs (tower order, big-endian) through the cooperative program
 API int hs_coop_verify_miller(const uint8_t* msg, size_t len, const uint8_t* sig, const uint8_t* pk, uint8_t* f_out) {
   ensure_init();

@@ -332,6 +332,22 @@ def test_cooperative_walk_matches_one_thread_walk(hs):
     assert hs.hs_walk4_matches(msg, len(msg), sig, bad_pk, ctypes.byref(st)) == 0 and st.value == O.verify(msg, sig, bad_pk) != 0
 
 
+def test_latency_layouts_of_the_machine(hs):
+    """coop_run_block12<2> / <3> (twelve / eighteen warps per group: the Karatsuba components of a row on different warps, exchanged
+    through shared memory) run as host threads with a std::barrier: verdicts = the oracle's."""
+    rng = random.Random(41)
+    sk = be(rng.randrange(1, R))
+    msg = rng.randbytes(32)
+    sig, pk = O.sign(msg, sk)[1], O.derive_pk_g2(sk)[1]
+    bad = O.g1_add(sig, G1_GEN)[1]
+    for split in (2, 3):
+        assert hs.hs_coop_verify_split(msg, len(msg), sig, pk, split) == 0
+        assert hs.hs_coop_verify_split(msg, len(msg), bad, pk, split) == O.VERIFICATION_FAILED
+        assert hs.hs_coop_verify_split(msg + b"!", len(msg) + 1, sig, pk, split) == O.VERIFICATION_FAILED
+        assert hs.hs_coop_verify_split(msg, len(msg), bytes(64), bytes(128), split) == 0   # both pairs skipped
+        assert hs.hs_coop_verify_split(msg, len(msg), sig, bytes(128), split) == O.VERIFICATION_FAILED
+
+
 def test_coop_multi_pairing_program(hs):
     """COOP_MULTI_K pairs per lane share one squaring chain, then the 32 lanes are multiplied by a butterfly: the block's
     product equals the oracle's Miller product over all pairs (canonical field values, any multiplication order)."""
