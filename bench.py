@@ -442,7 +442,8 @@ def run_engine(args):
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
         "data": "synthetic",
         "config": shared_config(n),
-        "engine": {"pairing_kernels": "cooperative machine: six warps per 32-item group, four groups per block (one per SM sub-partition), workspace chunks of 2^19 items"},
+        "engine": {"pairing_kernels": "cooperative machine: six warps per 32-item group, four groups per block (one per SM sub-partition), workspace chunks of 2^19 items",
+                   "small_batches": "counter-parallel hash, four-warp cooperative G2 walk, eighteen-warp machine blocks, producer and machine pipelined (latency_verify_host_buffers)"},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 224 * n, "d2h_bytes_per_step": n, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches, "clocks": sampler.result(), "roofline": roof,
         "cpu_baseline": cpu_line, "configs": configs,
