@@ -346,6 +346,72 @@ BN_FN void fq9_addk_sub(uint32_t (&t)[9], const fq& a, const uint32_t (&K)[8], c
   }
 #endif
 }
+// t += a + s on nine limbs, s a SIGNED small word (0, -1, -2 as 0xffffffff, 0xfffffffe: sign-extended into the ninth limb)
+BN_FN void fq9_add(uint32_t (&t)[9], const fq& a, uint32_t s) {
+#if defined(__CUDA_ARCH__)
+  const uint32_t sx = (uint32_t)((int32_t)s >> 31);
+  asm("add.cc.u32 %0, %0, %9;\n\t"
+      "addc.cc.u32 %1, %1, %10;\n\t"
+      "addc.cc.u32 %2, %2, %11;\n\t"
+      "addc.cc.u32 %3, %3, %12;\n\t"
+      "addc.cc.u32 %4, %4, %13;\n\t"
+      "addc.cc.u32 %5, %5, %14;\n\t"
+      "addc.cc.u32 %6, %6, %15;\n\t"
+      "addc.cc.u32 %7, %7, %16;\n\t"
+      "addc.u32 %8, %8, 0;\n\t"
+      : "+r"(t[0]), "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]), "+r"(t[8])
+      : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]));
+  asm("add.cc.u32 %0, %0, %9;\n\t"
+      "addc.cc.u32 %1, %1, %10;\n\t"
+      "addc.cc.u32 %2, %2, %10;\n\t"
+      "addc.cc.u32 %3, %3, %10;\n\t"
+      "addc.cc.u32 %4, %4, %10;\n\t"
+      "addc.cc.u32 %5, %5, %10;\n\t"
+      "addc.cc.u32 %6, %6, %10;\n\t"
+      "addc.cc.u32 %7, %7, %10;\n\t"
+      "addc.u32 %8, %8, %10;\n\t"
+      : "+r"(t[0]), "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]), "+r"(t[8])
+      : "r"(s), "r"(sx));
+#else
+  int64_t c = (int64_t)(int32_t)s;
+  for (int i = 0; i < 9; i++) {
+    c += (int64_t)t[i] + (int64_t)(i < 8 ? a.l[i] : 0);
+    t[i] = (uint32_t)c;
+    c >>= 32;
+  }
+#endif
+}
+// r = a + b mod 2^256; returns the carry
+BN_FN uint32_t fq_add_carry(fq& r, const fq& a, const fq& b) {
+  uint32_t cy;
+#if defined(__CUDA_ARCH__)
+  fq s;
+  asm("add.cc.u32 %0, %9, %17;\n\t"
+      "addc.cc.u32 %1, %10, %18;\n\t"
+      "addc.cc.u32 %2, %11, %19;\n\t"
+      "addc.cc.u32 %3, %12, %20;\n\t"
+      "addc.cc.u32 %4, %13, %21;\n\t"
+      "addc.cc.u32 %5, %14, %22;\n\t"
+      "addc.cc.u32 %6, %15, %23;\n\t"
+      "addc.cc.u32 %7, %16, %24;\n\t"
+      "addc.u32 %8, 0, 0;\n\t"
+      : "=&r"(s.l[0]), "=&r"(s.l[1]), "=&r"(s.l[2]), "=&r"(s.l[3]), "=&r"(s.l[4]), "=&r"(s.l[5]), "=&r"(s.l[6]), "=&r"(s.l[7]), "=&r"(cy)
+      : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]),
+        "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
+  r = s;
+#else
+  uint64_t c = 0;
+  fq s;
+  for (int i = 0; i < 8; i++) {
+    c += (uint64_t)a.l[i] + b.l[i];
+    s.l[i] = (uint32_t)c;
+    c >>= 32;
+  }
+  cy = (uint32_t)c;
+  r = s;
+#endif
+  return cy;
+}
 // a + b as a 256-bit number (no reduction; the caller knows it fits)
 BN_FN fq fq_add_raw(const fq& a, const fq& b) {
   fq s;

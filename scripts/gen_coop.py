@@ -150,6 +150,44 @@ def gen_mac():
     o.append("  fq r;\n")
     o.append("#pragma unroll\n  for (int k = 0; k < 8; k++) r.l[k] = e[k];\n")
     o.append("  return r;  // not yet canonical: the caller subtracts q once or twice\n}\n")
+    # ---- the accumulator as two plain 256-bit halves (no reduction): T = L + H * 2^256
+    o.append("// The accumulator as two plain halves, T = L + H * 2^256 (H takes the carry counters).  With the halves of the three Karatsuba\n")
+    o.append("// components in hand, ONE reduction per Fq2 coefficient is enough: REDC is linear, (T0 - T1) / 2^256 = redc_low(L0 - L1 mod 2^256)\n")
+    o.append("// + H0 - H1 - borrow (mod q), and the high halves are only added and subtracted (coop.cuh coop_dot_block).\n")
+    o.append("BN_FN void wide_split(const uint64_t (&E)[8], const uint64_t (&O)[8], const uint32_t (&C)[8], uint32_t (&L)[8], uint32_t (&H)[8]) {\n")
+    o.append("  uint32_t t[16];\n")
+    lines = []
+    for w in range(16):
+        op = "add.cc.u32" if w == 1 else ("addc.u32" if w == 15 else "addc.cc.u32")
+        if w == 0:
+            continue
+        lines.append((op, ["t[%d]" % w, "x[%d]" % w, "y[%d]" % (w - 1)]))
+    o.append("  uint32_t x[16], y[15];\n")
+    for w in range(16):
+        o.append("  x[%d] = %s;\n" % (w, word("E", w)))
+    for u in range(15):
+        o.append("  y[%d] = %s;\n" % (u, word("O", u)))
+    o.append("  t[0] = x[0];\n")
+    body = []
+    outs = ["t[%d]" % w for w in range(1, 16)]
+    ins_ = ["x[%d]" % w for w in range(1, 16)] + ["y[%d]" % u for u in range(15)]
+    ops_ = {}
+    for i, oo in enumerate(outs):
+        ops_[oo] = "%%%d" % i
+    for j, oo in enumerate(ins_):
+        ops_[oo] = "%%%d" % (len(outs) + j)
+    for op, args in lines:
+        body.append('"%s %s;\\n\\t"' % (op, ", ".join(ops_[a] for a in args)))
+    o.append("  asm(" + "\n      ".join(body) + "\n      : " + ", ".join('"=&r"(%s)' % oo for oo in outs))
+    o.append("\n      : " + ", ".join('"r"(%s)' % oo for oo in ins_) + ");\n")
+    # counters into the high half: C[j] -> limb 8+2j, C[4+j] -> limb 9+2j
+    body = []
+    for k in range(8):
+        op = "add.cc.u32" if k == 0 else ("addc.u32" if k == 7 else "addc.cc.u32")
+        body.append('"%s %%%d, %%%d, %%%d;\\n\\t"' % (op, k, k, 8 + k))
+    o.append("  asm(" + "\n      ".join(body) + "\n      : " + ", ".join('"+r"(t[%d])' % (8 + k) for k in range(8)))
+    o.append("\n      : " + ", ".join('"r"(C[%d])' % ((k // 2) if k % 2 == 0 else (4 + k // 2)) for k in range(8)) + ");\n")
+    o.append("#pragma unroll\n  for (int k = 0; k < 8; k++) {\n    L[k] = t[k];\n    H[k] = t[8 + k];\n  }\n}\n")
     o.append("#else\n")
     o.append("""// portable form (host simulation): the whole accumulator lives in E as 16 limbs
 BN_FN uint32_t wide_limb(const uint64_t (&E)[8], int w) { return (uint32_t)(E[w >> 1] >> (32 * (w & 1))); }
@@ -183,7 +221,13 @@ BN_FN fq wide_redc(uint64_t (&E)[8], uint64_t (&O)[8], uint32_t (&C)[8]) {
   return r;
 }
 """)
+    o.append("BN_FN void wide_split(const uint64_t (&E)[8], const uint64_t (&O)[8], const uint32_t (&C)[8], uint32_t (&L)[8], uint32_t (&H)[8]) {\n")
+    o.append("  (void)O;\n  (void)C;\n  for (int k = 0; k < 8; k++) {\n    L[k] = wide_limb(E, k);\n    H[k] = wide_limb(E, 8 + k);\n  }\n}\n")
     o.append("#endif\n\n")
+    o.append("// (L + m q) / 2^256 for a plain 256-bit L, m = -L / q mod 2^256: an integer in [0, q]\n")
+    o.append("BN_FN fq redc_low(const uint32_t (&L)[8]) {\n  uint64_t E[8], O[8];\n  uint32_t C[8];\n")
+    o.append("#if defined(__CUDA_ARCH__)\n#pragma unroll\n#endif\n  for (int i = 0; i < 8; i++) {\n    E[i] = i < 4 ? ((uint64_t)L[2 * i] | ((uint64_t)L[2 * i + 1] << 32)) : 0;\n    O[i] = 0;\n    C[i] = 0;\n  }\n")
+    o.append("  return wide_redc(E, O, C);\n}\n\n")
     o.append("// one Montgomery product through the accumulator (fq.cuh BN_FQ_MUL_WIDE): T = a b < q^2, REDC leaves less than 1.19 q\n")
     o.append("BN_FN fq fq_mul_wide(const fq& a, const fq& b) {\n  uint64_t E[8], O[8];\n  uint32_t C[8];\n")
     o.append("#if defined(__CUDA_ARCH__)\n#pragma unroll\n#endif\n  for (int i = 0; i < 8; i++) {\n    E[i] = 0;\n    O[i] = 0;\n    C[i] = 0;\n  }\n")
