@@ -346,6 +346,31 @@ BN_FN void fq9_addk_sub(uint32_t (&t)[9], const fq& a, const uint32_t (&K)[8], c
   }
 #endif
 }
+// d = a - b mod 2^256; returns 0 or 0xffffffff (the borrow, as a signed word)
+BN_FN uint32_t fq_sub_borrow(fq& d, const fq& a, const fq& b) {
+  uint32_t bw;
+#if defined(__CUDA_ARCH__)
+  fq r;
+  asm("sub.cc.u32 %0, %9, %17;\n\t"
+      "subc.cc.u32 %1, %10, %18;\n\t"
+      "subc.cc.u32 %2, %11, %19;\n\t"
+      "subc.cc.u32 %3, %12, %20;\n\t"
+      "subc.cc.u32 %4, %13, %21;\n\t"
+      "subc.cc.u32 %5, %14, %22;\n\t"
+      "subc.cc.u32 %6, %15, %23;\n\t"
+      "subc.cc.u32 %7, %16, %24;\n\t"
+      "subc.u32 %8, 0, 0;\n\t"
+      : "=&r"(r.l[0]), "=&r"(r.l[1]), "=&r"(r.l[2]), "=&r"(r.l[3]), "=&r"(r.l[4]), "=&r"(r.l[5]), "=&r"(r.l[6]), "=&r"(r.l[7]), "=&r"(bw)
+      : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]),
+        "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
+  d = r;
+#else
+  fq r;
+  bw = 0u - u256_sub(r.l, a.l, b.l);
+  d = r;
+#endif
+  return bw;
+}
 // t += a + s on nine limbs, s a SIGNED small word (0, -1, -2 as 0xffffffff, 0xfffffffe: sign-extended into the ninth limb)
 BN_FN void fq9_add(uint32_t (&t)[9], const fq& a, uint32_t s) {
 #if defined(__CUDA_ARCH__)
